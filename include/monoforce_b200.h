@@ -1,0 +1,133 @@
+/* monoforce_b200 C ABI  --  the drop-in boundary of the B200-native DPhysics rollout.
+ *
+ * The reference (ctu-vras/monoforce) is pure Python and has no FFI; the interface these
+ * entry points replace is the tensor-level contract of
+ *     DPhysics.forward / DPhysics.dphysics            monoforce/src/monoforce/models/traj_predictor/dphysics.py:596-605, :530-594
+ *     its implicit autograd backward                  
+ *     the per-trajectory path cost                    monoforce_ros/nodes/monoforce_node.py:91
+ * One call == one whole rollout of B trajectories x T steps.  All pointers are plain device
+ * (or, for the *_host entry points, host) pointers to dense row-major arrays of the scalar
+ * type selected by `dtype`; no torch types cross this boundary.  monoforce_b200/_lib.py is
+ * the ctypes binding; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Every function returns 0 on success and a negative mfb_status otherwise;
+ * mfb_last_error() returns a thread-local, human-readable description of the last failure.
+ */
+#ifndef MONOFORCE_B200_H_
+#define MONOFORCE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFB_ABI_VERSION 1
+
+typedef enum mfb_status {
+    MFB_OK = 0,
+    MFB_ERR_INVALID_ARGUMENT = -1,
+    MFB_ERR_UNSUPPORTED = -2,
+    MFB_ERR_CUDA = -3
+} mfb_status;
+
+typedef enum mfb_dtype { MFB_F32 = 0, MFB_F64 = 1 } mfb_dtype;
+
+/* Integrator variants of the reference. */
+typedef enum mfb_variant {
+    MFB_STEP_LOOP = 0,     /* DPhysics.dynamics, semi-implicit Euler + Rodrigues     dphysics.py:467-497 */
+    MFB_ODEINT_EULER = 1   /* DPhysics.dynamics_odeint, torchdiffeq fixed-grid Euler dphysics.py:499-528 */
+} mfb_variant;
+
+/* Problem description: sizes + the constants the reference reads from DPhysConfig
+ * (dphys_config.py:77-153).  Doubles are converted to the working precision inside the
+ * library exactly the way torch converts Python scalars. */
+typedef struct mfb_rollout_desc {
+    int32_t B;            /* trajectories                                             */
+    int32_t T;            /* recorded time indices (N_ts, dphysics.py:573)            */
+    int32_t N;            /* contact points (<= 256)                                  */
+    int32_t H, W;         /* height-map size; the reference requires H == W           */
+    int32_t n_tracks;     /* 2 or 4 driving parts (dphysics.py:75-104)                */
+    int32_t variant;      /* mfb_variant                                              */
+    int32_t reserved;
+    int64_t map_stride;   /* elements between consecutive trajectories' maps; 0 = all trajectories share one map */
+    double mass, gravity, stiffness, damping, grid_res, d_max, dt, omega_max;
+    double robot_Ly;      /* robot_size[1] (track gauge), dphys_config.py:43          */
+    double I_inv[9];      /* inverse of the body-frame inertia tensor, row-major (dphysics.py:152-153) */
+} mfb_rollout_desc;
+
+/* Inputs and outputs of the forward rollout.  Shapes follow DPhysics.forward. */
+typedef struct mfb_rollout_buffers {
+    /* inputs */
+    const void* z_grid;     /* (B or 1, H, W) height map(s)                           */
+    const void* friction;   /* (B or 1, H, W) friction map(s)                         */
+    const void* controls;   /* (B, T, 2) (v, w) per step                              */
+    const void* x0;         /* (B, 3)   initial position  (z component is overwritten by the start-height snap, see x0z) */
+    const void* xd0;        /* (B, 3)   initial velocity                              */
+    const void* R0;         /* (B, 3, 3) initial rotation                             */
+    const void* omega0;     /* (B, 3)   initial angular velocity                      */
+    const void* points;     /* (N, 3)   body-frame contact points                     */
+    const int32_t* part_id; /* (N,)     driving part of each point or -1              */
+    const void* ts;         /* (T,)     solver time grid; required for MFB_ODEINT_EULER, else may be NULL */
+    /* outputs */
+    void* Xs;               /* (B, T, 3)                                              */
+    void* Xds;              /* (B, T, 3)                                              */
+    void* Rs;               /* (B, T, 3, 3)                                           */
+    void* Omegas;           /* (B, T, 3)                                              */
+    void* F_springs;        /* (B, T, N, 3) or NULL: do not materialise forces        */
+    void* F_frictions;      /* (B, T, N, 3) or NULL (must be NULL iff F_springs is)   */
+    void* x0z;              /* (B,)  start height written by the snap (dphysics.py:567-571) */
+    void* cost;             /* (B,)  or NULL: std_t(std_p |F_spring|), step-loop variant only */
+} mfb_rollout_buffers;
+
+/* Gradients for the adjoint (reverse-time) pass.  NULL input gradients are treated as zero;
+ * NULL output gradients are not computed. */
+typedef struct mfb_rollout_grads {
+    /* incoming: d loss / d output */
+    const void* g_Xs;         /* (B, T, 3)    */
+    const void* g_Xds;        /* (B, T, 3)    */
+    const void* g_Rs;         /* (B, T, 3, 3) */
+    const void* g_Omegas;     /* (B, T, 3)    */
+    const void* g_F_springs;  /* (B, T, N, 3) */
+    const void* g_F_frictions;/* (B, T, N, 3) */
+    const void* g_x0z;        /* (B,) gradient w.r.t. the snapped start height output */
+    /* outgoing: d loss / d input.  Map gradients are ACCUMULATED (+=) into zero-initialised buffers. */
+    void* g_z_grid;           /* (B or 1, H, W) */
+    void* g_friction;         /* (B or 1, H, W) */
+    void* g_controls;         /* (B, T, 2)      */
+    void* g_x0;               /* (B, 3)  (z component is always 0: the snap overwrites it) */
+    void* g_xd0;              /* (B, 3)         */
+    void* g_R0;               /* (B, 3, 3)      */
+    void* g_omega0;           /* (B, 3)         */
+} mfb_rollout_grads;
+
+/* ---- device-pointer entry points (asynchronous on `stream`, a cudaStream_t) ------------ */
+
+/* Replaces DPhysics.dphysics (dphysics.py:530-594): snap, T fused steps, post-processing. */
+int mfb_rollout_forward(const mfb_rollout_desc* desc, const mfb_rollout_buffers* io,
+                        int dtype, void* stream);
+
+/* Replaces autograd's backward through DPhysics.dphysics.  `io` must
+ * hold the forward inputs and the recorded states (Xs, Xds, Rs, Omegas) of the same call. */
+int mfb_rollout_backward(const mfb_rollout_desc* desc, const mfb_rollout_buffers* io,
+                         const mfb_rollout_grads* grads, int dtype, void* stream);
+
+/* ---- host-pointer entry point (synchronous; copies in, launches, copies out) ----------- */
+
+/* Same contract as mfb_rollout_forward with HOST buffers; NULL outputs are skipped.
+ * Device scratch is cached inside the library between calls. */
+int mfb_rollout_forward_host(const mfb_rollout_desc* desc, const mfb_rollout_buffers* io,
+                             int dtype, int device);
+
+/* ---- bookkeeping ------------------------------------------------------------------------- */
+const char* mfb_last_error(void);
+int mfb_abi_version(void);
+/* Number of CUDA kernels this library has launched since load (monotonic). */
+long long mfb_kernel_launches(void);
+/* Frees the cached device scratch of mfb_rollout_forward_host. */
+void mfb_release_scratch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONOFORCE_B200_H_ */

