@@ -115,7 +115,8 @@ class _Rollout(torch.autograd.Function):
         dev = z.device
         B, T, N = meta.B, meta.T, meta.N
         z, mu, controls = z.contiguous(), mu.contiguous(), controls.contiguous()
-        x0, xd0, R0, om0 = x0.contiguous(), xd0.contiguous(), R0.contiguous(), om0.contiguous()
+        # x0 is cloned: the caller's tensor is overwritten in place afterwards (start-height snap, :571)
+        x0, xd0, R0, om0 = x0.contiguous().clone(), xd0.contiguous(), R0.contiguous(), om0.contiguous()
         new = lambda *s: torch.empty(*s, dtype=dt_, device=dev)
         Xs, Xds, Rs, Oms = new(B, T, 3), new(B, T, 3), new(B, T, 3, 3), new(B, T, 3)
         Fs = new(B, T, N, 3) if meta.want_forces else None

@@ -55,6 +55,13 @@ def forward_case(dp, cfgm, name, robot, grid_res, T, B, terrain, variant="step",
     sim = dp.DPhysics(cfg)
     if terrain == "flat":
         z = torch.zeros_like(cfg.x_grid)
+    elif terrain == "ramp":
+        # Diagonal ramp z = 0.25 (x + y): the only sloped terrain on which the reference's sampling
+        # (x+1 / y+1 neighbours carry each other's weight, dphysics.py:442-445) is CONTINUOUS across
+        # cell borders.  Elsewhere a contact point crossing a border gets a height jump of
+        # z[i,j+1] - z[i+1,j], so two fp32 implementations that differ by one ulp in the point
+        # position can disagree about the step at which the jump happens (parity).
+        z = 0.25 * (cfg.x_grid + cfg.y_grid)
     elif terrain == "hill":
         z = hill(cfg)
     else:
@@ -154,6 +161,9 @@ def main():
                  given_state=True, fric=True, seed=3)
     forward_case(dp, cfgm, "marv_flat256_T400_B2", "marv", 0.05, 400, 2, "flat", seed=4)
     forward_case(dp, cfgm, "marv_hill128_odeint_T60_B2", "marv", 0.1, 60, 2, "hill", variant="odeint", seed=5)
+    forward_case(dp, cfgm, "marv_ramp128_odeint_T200_B3", "marv", 0.1, 200, 3, "ramp", variant="odeint", seed=9)
+    forward_case(dp, cfgm, "marv_ramp256_T400_B3", "marv", 0.05, 400, 3, "ramp", seed=10)
+    forward_case(dp, cfgm, "tradr_ramp128_T300_B3", "tradr", 0.1, 300, 3, "ramp", seed=11)
     forward_case(dp, cfgm, "marv_hill128_joints_T60_B2", "marv", 0.1, 60, 2, "hill", joints=True, seed=6)
     grad_case(dp, cfgm, "grad64_marv_noise128_T40_B2", "marv", 0.1, 40, 2, seed=7)
     grad_case(dp, cfgm, "grad64_tradr_noise64_T40_B2", "tradr", 0.2, 40, 2, seed=8)

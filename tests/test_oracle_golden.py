@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, make_spec
+from helpers_mfb import load_golden, make_spec
 
 
 def _cfg(g):
@@ -15,7 +15,7 @@ def _cfg(g):
 
 FWD = ["cfg1_marv_flat64_T100", "cfg1_tradr_flat64_T100", "marv_hill128_T100_B4", "marv_noise128_state_fric_T100_B4",
        "tradr_noise128_state_fric_T100_B4", "marv_flat256_T400_B2", "marv_hill128_odeint_T60_B2",
-       "marv_hill128_joints_T60_B2"]
+       "marv_hill128_joints_T60_B2", "marv_ramp128_odeint_T200_B3", "marv_ramp256_T400_B3", "tradr_ramp128_T300_B3"]
 
 
 @pytest.mark.parametrize("name", FWD)

@@ -1,9 +1,10 @@
 """Scratch timing of the rollout kernels at BASELINE config 2/3 size (not the bench)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+_R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _R); sys.path.insert(0, os.path.join(_R, 'tests'))
 import torch
 from monoforce_b200 import DPhysics, DPhysConfig
-from tests.conftest import hill_map
+from helpers_mfb import hill_map
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 T = 400
