@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--traj-per-gpu", type=int, default=4096)
-    ap.add_argument("--cpu-sample", type=int, default=32, help="trajectories per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="trajectories per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -78,6 +78,10 @@ typedef struct mfb_rollout_buffers {
     void* F_frictions;      /* (B, T, N, 3) or NULL (must be NULL iff F_springs is)   */
     void* x0z;              /* (B,)  start height written by the snap (dphysics.py:567-571) */
     void* cost;             /* (B,)  or NULL: std_t(std_p |F_spring|), step-loop variant only */
+    /* scratch */
+    void* workspace;        /* device scratch of at least mfb_rollout_workspace_bytes(); holds the packed
+                               per-cell sampling table the kernels build from z_grid / friction on every call */
+    int64_t workspace_bytes;
 } mfb_rollout_buffers;
 
 /* Gradients for the adjoint (reverse-time) pass.  NULL input gradients are treated as zero;
@@ -102,6 +106,10 @@ typedef struct mfb_rollout_grads {
 } mfb_rollout_grads;
 
 /* ---- device-pointer entry points (asynchronous on `stream`, a cudaStream_t) ------------ */
+
+/* Bytes of device scratch mfb_rollout_forward / mfb_rollout_backward need for `desc` (16-byte
+ * aligned base required): one 12-scalar record per map cell, per distinct map. */
+int64_t mfb_rollout_workspace_bytes(const mfb_rollout_desc* desc, int dtype);
 
 /* Replaces DPhysics.dphysics (dphysics.py:530-594): snap, T fused steps, post-processing. */
 int mfb_rollout_forward(const mfb_rollout_desc* desc, const mfb_rollout_buffers* io,

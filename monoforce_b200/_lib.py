@@ -15,7 +15,7 @@ MFB_F32, MFB_F64 = 0, 1
 MFB_STEP_LOOP, MFB_ODEINT_EULER = 0, 1
 
 EXPORTED_SYMBOLS = (
-    "mfb_rollout_forward", "mfb_rollout_backward", "mfb_rollout_forward_host",
+    "mfb_rollout_workspace_bytes", "mfb_rollout_forward", "mfb_rollout_backward", "mfb_rollout_forward_host",
     "mfb_last_error", "mfb_abi_version", "mfb_kernel_launches", "mfb_release_scratch",
 )
 
@@ -37,7 +37,7 @@ _OUT = ("Xs", "Xds", "Rs", "Omegas", "F_springs", "F_frictions", "x0z", "cost")
 
 
 class RolloutBuffers(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in _IN + _OUT]
+    _fields_ = [(n, C.c_void_p) for n in _IN + _OUT] + [("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
 _GIN = ("g_Xs", "g_Xds", "g_Rs", "g_Omegas", "g_F_springs", "g_F_frictions", "g_x0z")
@@ -68,6 +68,8 @@ def load() -> C.CDLL:
     lib.mfb_rollout_backward.restype = C.c_int
     lib.mfb_rollout_forward_host.argtypes = [C.POINTER(RolloutDesc), C.POINTER(RolloutBuffers), C.c_int, C.c_int]
     lib.mfb_rollout_forward_host.restype = C.c_int
+    lib.mfb_rollout_workspace_bytes.argtypes = [C.POINTER(RolloutDesc), C.c_int]
+    lib.mfb_rollout_workspace_bytes.restype = C.c_int64
     lib.mfb_last_error.restype = C.c_char_p
     lib.mfb_abi_version.restype = C.c_int
     lib.mfb_kernel_launches.restype = C.c_longlong

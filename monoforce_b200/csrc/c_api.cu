@@ -1,6 +1,7 @@
 // C ABI of libmonoforce_b200.so (declared in include/monoforce_b200.h).
 // Validates the descriptor, converts the constants to the working precision the way torch
 // converts python scalars, and dispatches to the sm_100a kernels.  No torch types here.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -60,6 +61,8 @@ static RolloutArgs<T> make_args(const mfb_rollout_desc& d, const mfb_rollout_buf
     a.z = (const T*)io.z_grid; a.mu = (const T*)io.friction; a.controls = (const T*)io.controls;
     a.x0 = (const T*)io.x0; a.xd0 = (const T*)io.xd0; a.R0 = (const T*)io.R0; a.om0 = (const T*)io.omega0;
     a.pts = (const T*)io.points; a.part = io.part_id; a.ts = (const T*)io.ts;
+    a.cells = (const T*)io.workspace;
+    a.cell_stride = d.map_stride == 0 ? 0 : (long long)d.H * d.W * kCellRec;
     a.Xs = (T*)io.Xs; a.Xds = (T*)io.Xds; a.Rs = (T*)io.Rs; a.Oms = (T*)io.Omegas;
     a.Fs = (T*)io.F_springs; a.Ff = (T*)io.F_frictions; a.x0z = (T*)io.x0z; a.cost = (T*)io.cost;
     return a;
@@ -77,9 +80,42 @@ static const char* check_io_forward(const mfb_rollout_desc& d, const mfb_rollout
     return nullptr;
 }
 
+// workspace layout: [cell table: n_maps*H*W*12 scalars][map-gradient scratch: n_maps*H*W*2 scalars]
+static long long table_elems(const mfb_rollout_desc& d) {
+    const long long n_maps = d.map_stride == 0 ? 1 : d.B;
+    return n_maps * d.H * d.W * kCellRec;
+}
+static long long workspace_bytes(const mfb_rollout_desc& d, int dtype) {
+    const long long n_maps = d.map_stride == 0 ? 1 : d.B;
+    return (table_elems(d) + n_maps * d.H * d.W * 2) * (dtype == MFB_F32 ? 4 : 8);
+}
+
+static const char* check_workspace(const mfb_rollout_desc& d, const mfb_rollout_buffers& io, int dtype) {
+    if (!io.workspace) return "workspace is NULL (see mfb_rollout_workspace_bytes)";
+    if (io.workspace_bytes < workspace_bytes(d, dtype)) return "workspace is smaller than mfb_rollout_workspace_bytes()";
+    if (((uintptr_t)io.workspace & 15) != 0) return "workspace must be 16-byte aligned";
+    return nullptr;
+}
+
+// K0: packed per-cell sampling table (one thread per cell), rebuilt on every call
+template <typename T>
+static int build_table(const mfb_rollout_desc& d, const mfb_rollout_buffers& io, cudaStream_t st) {
+    const int n_maps = d.map_stride == 0 ? 1 : d.B;
+    const long long total = (long long)n_maps * d.H * d.W;
+    const int block = 256;
+    const int grid = (int)std::min<long long>((total + block - 1) / block, 148 * 32);
+    build_cell_table_kernel<T><<<grid, block, 0, st>>>((const T*)io.z_grid, (const T*)io.friction, (T*)io.workspace, n_maps,
+                                                       d.H, d.W, d.map_stride, (T)1 / (T)d.grid_res);
+    count_launch();
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return fail(MFB_ERR_CUDA, std::string("build_cell_table launch: ") + cudaGetErrorString(ce));
+    return MFB_OK;
+}
+
 template <typename T>
 static int forward_typed(const mfb_rollout_desc& d, const mfb_rollout_buffers& io, cudaStream_t st) {
     RolloutArgs<T> a = make_args<T>(d, io);
+    if (int rc = build_table<T>(d, io, st)) return rc;
     LaunchError e = d.variant == MFB_STEP_LOOP ? launch_rollout_fwd<T, kStepLoop>(a, st)
                                                : launch_rollout_fwd<T, kOdeintEuler>(a, st);
     if (e.msg) return fail(MFB_ERR_UNSUPPORTED, e.msg);
@@ -92,16 +128,34 @@ template <typename T>
 static int backward_typed(const mfb_rollout_desc& d, const mfb_rollout_buffers& io, const mfb_rollout_grads& g,
                           cudaStream_t st) {
     RolloutArgs<T> a = make_args<T>(d, io);
+    if (int rc = build_table<T>(d, io, st)) return rc;
     AdjointArgs<T> ga;
     ga.g_Xs = (const T*)g.g_Xs; ga.g_Xds = (const T*)g.g_Xds; ga.g_Rs = (const T*)g.g_Rs; ga.g_Oms = (const T*)g.g_Omegas;
     ga.g_Fs = (const T*)g.g_F_springs; ga.g_Ff = (const T*)g.g_F_frictions; ga.g_x0z = (const T*)g.g_x0z;
-    ga.g_z = (T*)g.g_z_grid; ga.g_mu = (T*)g.g_friction; ga.g_controls = (T*)g.g_controls;
+    const long long n_maps = d.map_stride == 0 ? 1 : d.B;
+    const long long cells_total = n_maps * d.H * d.W;
+    const bool want_maps = g.g_z_grid || g.g_friction;
+    if (want_maps && d.map_stride != 0 && d.map_stride != (long long)d.H * d.W)
+        return fail(MFB_ERR_UNSUPPORTED, "map gradients need densely packed per-trajectory maps (map_stride == H*W)");
+    T* scratch = (T*)io.workspace + table_elems(d);
+    ga.g_maps = want_maps ? scratch : nullptr;
+    ga.g_maps_stride = d.map_stride == 0 ? 0 : (long long)d.H * d.W * 2;
+    if (want_maps) {
+        cudaError_t me = cudaMemsetAsync(scratch, 0, (size_t)cells_total * 2 * sizeof(T), st);
+        if (me != cudaSuccess) return fail(MFB_ERR_CUDA, std::string("memset grad scratch: ") + cudaGetErrorString(me));
+    }
+    ga.g_controls = (T*)g.g_controls;
     ga.g_x0 = (T*)g.g_x0; ga.g_xd0 = (T*)g.g_xd0; ga.g_R0 = (T*)g.g_R0; ga.g_om0 = (T*)g.g_omega0;
     LaunchError e = d.variant == MFB_STEP_LOOP ? launch_rollout_bwd<T, kStepLoop>(a, ga, st)
                                                : launch_rollout_bwd<T, kOdeintEuler>(a, ga, st);
     if (e.msg) return fail(MFB_ERR_UNSUPPORTED, e.msg);
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(MFB_ERR_CUDA, std::string("rollout_bwd launch: ") + cudaGetErrorString(ce));
+    if (want_maps) {
+        launch_scatter_map_grads<T, kStepLoop>(scratch, (T*)g.g_z_grid, (T*)g.g_friction, cells_total, st);
+        ce = cudaGetLastError();
+        if (ce != cudaSuccess) return fail(MFB_ERR_CUDA, std::string("scatter_map_grads launch: ") + cudaGetErrorString(ce));
+    }
     return MFB_OK;
 }
 
@@ -126,6 +180,8 @@ extern "C" {
 int mfb_rollout_forward(const mfb_rollout_desc* desc, const mfb_rollout_buffers* io, int dtype, void* stream) {
     if (const char* m = check_desc(desc)) return fail(MFB_ERR_INVALID_ARGUMENT, m);
     if (const char* m = check_io_forward(*desc, io)) return fail(MFB_ERR_INVALID_ARGUMENT, m);
+    if (dtype != MFB_F32 && dtype != MFB_F64) return fail(MFB_ERR_INVALID_ARGUMENT, "dtype must be MFB_F32 or MFB_F64");
+    if (const char* m = check_workspace(*desc, *io, dtype)) return fail(MFB_ERR_INVALID_ARGUMENT, m);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MFB_F32) return forward_typed<float>(*desc, *io, st);
     if (dtype == MFB_F64) return forward_typed<double>(*desc, *io, st);
@@ -140,6 +196,8 @@ int mfb_rollout_backward(const mfb_rollout_desc* desc, const mfb_rollout_buffers
         !io->points || !io->part_id || !io->Xs || !io->Xds || !io->Rs || !io->Omegas || !io->x0z)
         return fail(MFB_ERR_INVALID_ARGUMENT, "backward needs the forward inputs and the recorded states");
     if (desc->variant == MFB_ODEINT_EULER && !io->ts) return fail(MFB_ERR_INVALID_ARGUMENT, "ts is required for the odeint variant");
+    if (dtype != MFB_F32 && dtype != MFB_F64) return fail(MFB_ERR_INVALID_ARGUMENT, "dtype must be MFB_F32 or MFB_F64");
+    if (const char* m = check_workspace(*desc, *io, dtype)) return fail(MFB_ERR_INVALID_ARGUMENT, m);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MFB_F32) return backward_typed<float>(*desc, *io, *grads, st);
     if (dtype == MFB_F64) return backward_typed<double>(*desc, *io, *grads, st);
@@ -173,6 +231,7 @@ int mfb_rollout_forward_host(const mfb_rollout_desc* desc, const mfb_rollout_buf
     Seg s_x0z = seg(B * es), s_cost = seg(B * es);
     const bool forces = io->F_springs != nullptr;
     Seg s_Fs = seg(forces ? B * T * N * 3 * es : 0), s_Ff = seg(forces ? B * T * N * 3 * es : 0);
+    Seg s_ws = seg((size_t)workspace_bytes(d, dtype));
 
     std::lock_guard<std::mutex> lock(g_scratch.mu);
     cudaError_t ce = cudaSetDevice(device);
@@ -203,6 +262,8 @@ int mfb_rollout_forward_host(const mfb_rollout_desc* desc, const mfb_rollout_buf
     dev.cost = io->cost ? base + s_cost.off : nullptr;
     dev.F_springs = forces ? base + s_Fs.off : nullptr;
     dev.F_frictions = forces ? base + s_Ff.off : nullptr;
+    dev.workspace = base + s_ws.off;
+    dev.workspace_bytes = (int64_t)s_ws.bytes;
 
     int rc = mfb_rollout_forward(desc, &dev, dtype, st);
     if (rc != MFB_OK) return rc;
@@ -212,6 +273,11 @@ int mfb_rollout_forward_host(const mfb_rollout_desc* desc, const mfb_rollout_buf
     ce = cudaStreamSynchronize(st);
     if (ce != cudaSuccess) return fail(MFB_ERR_CUDA, std::string("rollout (host entry): ") + cudaGetErrorString(ce));
     return MFB_OK;
+}
+
+int64_t mfb_rollout_workspace_bytes(const mfb_rollout_desc* desc, int dtype) {
+    if (check_desc(desc) || (dtype != MFB_F32 && dtype != MFB_F64)) return -1;
+    return workspace_bytes(*desc, dtype);
 }
 
 const char* mfb_last_error(void) { return g_err.c_str(); }

@@ -17,6 +17,10 @@ template <typename T> struct AdjointArgs;
 template <typename T, int VARIANT>
 LaunchError launch_rollout_bwd(const RolloutArgs<T>& args, const AdjointArgs<T>& g, cudaStream_t stream);
 
+// adds the interleaved (z, mu) gradient scratch into the caller's maps (instantiated next to the kernels)
+template <typename T, int VARIANT>
+void launch_scatter_map_grads(const T* g2, T* g_z, T* g_mu, long long n, cudaStream_t stream);
+
 void count_launch();
 
 }  // namespace mfb

@@ -12,10 +12,17 @@ namespace mfb {
 template <typename T, int PPL, int VARIANT>
 static LaunchError launch_ppl(const RolloutArgs<T>& a, const AdjointArgs<T>& g, cudaStream_t st) {
     const dim3 grid((a.B + kBwdWarps - 1) / kBwdWarps), block(kBwdWarps * 32);
-    if (g.g_Fs || g.g_Ff) rollout_bwd_kernel<T, PPL, VARIANT, true><<<grid, block, 0, st>>>(a, g);
-    else                  rollout_bwd_kernel<T, PPL, VARIANT, false><<<grid, block, 0, st>>>(a, g);
-    count_launch();
-    return {nullptr};
+    const size_t smem = g.g_maps ? kBwdWarps * sizeof(MapGradCache<T>) : 0;
+    auto go = [&](auto kern) -> LaunchError {
+        if (smem > 0 &&
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return {"cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"};
+        kern<<<grid, block, smem, st>>>(a, g);
+        count_launch();
+        return {nullptr};
+    };
+    if (g.g_Fs || g.g_Ff) return go(rollout_bwd_kernel<T, PPL, VARIANT, true>);
+    return go(rollout_bwd_kernel<T, PPL, VARIANT, false>);
 }
 
 template <>
@@ -35,6 +42,15 @@ LaunchError launch_rollout_bwd<MFB_INST_T, MFB_INST_VARIANT>(const RolloutArgs<M
         case 8: return launch_ppl<T, 8, V>(a, g, st);
         default: return {"number of contact points must be in [1, 256]"};
     }
+}
+
+template <>
+void launch_scatter_map_grads<MFB_INST_T, MFB_INST_VARIANT>(const MFB_INST_T* g2, MFB_INST_T* g_z, MFB_INST_T* g_mu,
+                                                            long long n, cudaStream_t st) {
+    const int block = 256;
+    const int grid = (int)((n + block - 1) / block < 148 * 16 ? (n + block - 1) / block : 148 * 16);
+    scatter_map_grads_kernel<MFB_INST_T><<<grid, block, 0, st>>>(g2, g_z, g_mu, n);
+    count_launch();
 }
 
 }  // namespace mfb

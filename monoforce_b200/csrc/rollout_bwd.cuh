@@ -18,6 +18,52 @@
 namespace mfb {
 
 constexpr int kBwdWarps = 4;
+#ifndef MFB_BWD_MINB
+#define MFB_BWD_MINB 3
+#endif
+
+// ------------------------------------------------------------------------------------------
+// map-gradient accumulation
+// ------------------------------------------------------------------------------------------
+// A contact point stays in the same map cell for several steps (<= 0.2 cells / step at 1 m/s,
+// 5 cm cells), so each lane keeps, per point, a private shared-memory accumulator of the eight
+// corner gradients (4 x height, 4 x friction) of its current cell and only flushes it to global
+// memory when the point moves to another cell: ~10x fewer global atomics than one per step.
+// The global target interleaves (d/dz, d/dfriction) per cell so a flush is two 16-byte or four
+// 8-byte vector reductions (red.global.add.v4.f32 / .v2.f32, sm_90+).
+template <typename T>
+struct MapGradCache {
+    int cell[kMaxPointsPerLane * 32];
+    T acc[8][kMaxPointsPerLane * 32];
+};
+
+__device__ __forceinline__ void red_pair(float* p, float a, float b) { atomicAdd(reinterpret_cast<float2*>(p), make_float2(a, b)); }
+__device__ __forceinline__ void red_pair(double* p, double a, double b) { atomicAdd(p, a); atomicAdd(p + 1, b); }
+__device__ __forceinline__ void red_quad(float* p, float a, float b, float c, float d) {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));
+}
+__device__ __forceinline__ void red_quad(double* p, double a, double b, double c, double d) {
+    atomicAdd(p, a); atomicAdd(p + 1, b); atomicAdd(p + 2, c); atomicAdd(p + 3, d);
+}
+
+// g: interleaved (z, mu) gradient map; v = {z00, z10, z01, z11, m00, m10, m01, m11}
+template <typename T>
+__device__ __forceinline__ void scatter_corners(T* __restrict__ g, const Corners& c, const T* v) {
+    // (k00, k01) and (k10, k11) are neighbours along y unless the flat clamp collapsed them
+    if (c.k01 == c.k00 + 1 && (c.k00 & 1) == 0) red_quad(g + 2 * (long long)c.k00, v[0], v[4], v[2], v[6]);
+    else { red_pair(g + 2 * (long long)c.k00, v[0], v[4]); red_pair(g + 2 * (long long)c.k01, v[2], v[6]); }
+    if (c.k11 == c.k10 + 1 && (c.k10 & 1) == 0) red_quad(g + 2 * (long long)c.k10, v[1], v[5], v[3], v[7]);
+    else { red_pair(g + 2 * (long long)c.k10, v[1], v[5]); red_pair(g + 2 * (long long)c.k11, v[3], v[7]); }
+}
+
+// adds (z, mu) gradient scratch into the caller's separate gradient maps
+template <typename T>
+__global__ void scatter_map_grads_kernel(const T* __restrict__ g2, T* __restrict__ g_z, T* __restrict__ g_mu, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (g_z) g_z[i] += g2[2 * i];
+        if (g_mu) g_mu[i] += g2[2 * i + 1];
+    }
+}
 
 template <typename T>
 __device__ __forceinline__ T gate(T grad, T val, T lim) {   // backward of clamp(val, -lim, lim)
@@ -60,7 +106,7 @@ __device__ __forceinline__ void rodrigues_right_bwd(const T* w, T dt, const T* E
 }
 
 template <typename T, int PPL, int VARIANT, bool HAS_FGRAD>
-__global__ void __launch_bounds__(kBwdWarps * 32)
+__global__ void __launch_bounds__(kBwdWarps * 32, (sizeof(T) == 4 && PPL <= 7) ? MFB_BWD_MINB : 1)
 rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
     __shared__ PointTable<T> tab;
     fill_point_table(tab, a, PPL * 32);
@@ -74,8 +120,14 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
 
     const T* __restrict__ zmap = a.z + (long long)b * a.map_stride;
     const T* __restrict__ fmap = a.mu + (long long)b * a.map_stride;
-    T* __restrict__ gz = g.g_z ? g.g_z + (long long)b * a.map_stride : nullptr;
-    T* __restrict__ gm = g.g_mu ? g.g_mu + (long long)b * a.map_stride : nullptr;
+    const T* __restrict__ cells = a.cells + (long long)b * a.cell_stride;
+    T* __restrict__ gmap = g.g_maps ? g.g_maps + (long long)b * g.g_maps_stride : nullptr;
+    extern __shared__ __align__(16) unsigned char cache_raw[];
+    MapGradCache<T>& wc = reinterpret_cast<MapGradCache<T>*>(cache_raw)[threadIdx.x >> 5];
+    if (gmap) {
+#pragma unroll
+        for (int j = 0; j < PPL; ++j) wc.cell[j * 32 + lane] = -1;
+    }
     const T* __restrict__ ctrl = a.controls + (long long)b * a.nT * 2;
     const int H = a.H, W = a.W;
     const long long rowF = (long long)a.N * 3;
@@ -249,13 +301,9 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
         }
         const T fs_b0 = vd_b[0] * a.inv_mass, fs_b1 = vd_b[1] * a.inv_mass, fs_b2 = vd_b[2] * a.inv_mass;
 
-        // thrust direction
-        T hd[3], hd_norm;
-        {
-            hd_norm = Mth<T>::sqrt_rn(s.R[0] * s.R[0] + s.R[3] * s.R[3] + s.R[6] * s.R[6]);
-            const T inv = (T)1 / Mth<T>::fmax_(hd_norm, (T)1e-6);
-            hd[0] = s.R[0] * inv; hd[1] = s.R[3] * inv; hd[2] = s.R[6] * inv;
-        }
+        StepFrame<T> f;
+        make_frame(f, s, uv, uw, a.d_max, a.res, a.inv_res);
+        const T hd_norm = Mth<T>::sqrt_rn(s.R[0] * s.R[0] + s.R[3] * s.R[3] + s.R[6] * s.R[6]);
 
         // ---------------- pass A: phase 1 forward ----------------
         T nrm[PPL][3], sc[PPL], slip[PPL][3], arm[PPL][3];
@@ -263,36 +311,13 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
             const int slot = j * 32 + lane;
-            const T px = tab.px[slot], py = tab.py[slot], pz = tab.pz[slot];
-            const T r0 = s.R[0] * px + s.R[1] * py + s.R[2] * pz;
-            const T r1 = s.R[3] * px + s.R[4] * py + s.R[5] * pz;
-            const T r2 = s.R[6] * px + s.R[7] * py + s.R[8] * pz;
-            const T Px = r0 + s.x[0], Py = r1 + s.x[1], Pz = r2 + s.x[2];
-            const T V0 = s.v[0] + (s.w[1] * r2 - s.w[2] * r1);
-            const T V1 = s.v[1] + (s.w[2] * r0 - s.w[0] * r2);
-            const T V2 = s.v[2] + (s.w[0] * r1 - s.w[1] * r0);
-            T fx, fy;
-            const Cell c = locate(Mth<T>::to_cells(Px, a.d_max, a.res, a.inv_res),
-                                  Mth<T>::to_cells(Py, a.d_max, a.res, a.inv_res), H, W, fx, fy);
-            const T z00 = ldg(zmap + c.k00), z10 = ldg(zmap + c.k10), z01 = ldg(zmap + c.k01), z11 = ldg(zmap + c.k11);
-            const T m00 = ldg(fmap + c.k00), m10 = ldg(fmap + c.k10), m01 = ldg(fmap + c.k01), m11 = ldg(fmap + c.k11);
-            const T zv = blend(fx, fy, z00, z10, z01, z11);
-            const T mu = blend(fx, fy, m00, m10, m01, m11);
-            const T ax = (z00 - z10) * a.inv_res, ay = (z00 - z01) * a.inv_res;
-            const T q = Mth<T>::rsqrt(ax * ax + ay * ay + (T)1);
-            const T n0 = ax * q, n1 = ay * q, n2 = q;
-            const T dh = Pz - zv;
-            T cw = Mth<T>::contact(dh);
-            if (j == PPL - 1 && !last_valid) cw = (T)0;
-            C += cw;
-            const T vn = V0 * n0 + V1 * n1 + V2 * n2;
-            sc[j] = -(a.stiffness * dh + a.damping * vn) * cw;
-            const T tau = tab.driven[slot] * uv + tab.side[slot] * uw;
-            const T d0 = mu * (tau * hd[0] - V0), d1 = mu * (tau * hd[1] - V1), d2 = mu * (tau * hd[2] - V2);
-            const T dn = d0 * n0 + d1 * n1 + d2 * n2;
-            slip[j][0] = d0 - dn * n0; slip[j][1] = d1 - dn * n1; slip[j][2] = d2 - dn * n2;
-            nrm[j][0] = n0; nrm[j][1] = n1; nrm[j][2] = n2;
-            arm[j][0] = r0; arm[j][1] = r1; arm[j][2] = r2;
+            PointEval<T> e;
+            eval_point(e, f, tab.px[slot], tab.py[slot], tab.pz[slot], tab.driven[slot], tab.side[slot],
+                       (j < PPL - 1) || last_valid, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
+            C += e.cw;
+            sc[j] = e.sp * e.cw;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { slip[j][k] = e.sl[k]; nrm[j][k] = e.rec[4 + k]; arm[j][k] = e.r[k]; }
         }
         C = warp_sum(C);
         const T invC = Mth<T>::rcp(C);
@@ -363,82 +388,75 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             const int slot = j * 32 + lane;
             const bool ok = (j < PPL - 1 || last_valid);
             const T px = tab.px[slot], py = tab.py[slot], pz = tab.pz[slot];
-            const T r0 = s.R[0] * px + s.R[1] * py + s.R[2] * pz;
-            const T r1 = s.R[3] * px + s.R[4] * py + s.R[5] * pz;
-            const T r2 = s.R[6] * px + s.R[7] * py + s.R[8] * pz;
-            const T Px = r0 + s.x[0], Py = r1 + s.x[1], Pz = r2 + s.x[2];
-            const T V0 = s.v[0] + (s.w[1] * r2 - s.w[2] * r1);
-            const T V1 = s.v[1] + (s.w[2] * r0 - s.w[0] * r2);
-            const T V2 = s.v[2] + (s.w[0] * r1 - s.w[1] * r0);
-            T fx, fy;
-            const Cell c = locate(Mth<T>::to_cells(Px, a.d_max, a.res, a.inv_res),
-                                  Mth<T>::to_cells(Py, a.d_max, a.res, a.inv_res), H, W, fx, fy);
-            const T z00 = ldg(zmap + c.k00), z10 = ldg(zmap + c.k10), z01 = ldg(zmap + c.k01), z11 = ldg(zmap + c.k11);
-            const T m00 = ldg(fmap + c.k00), m10 = ldg(fmap + c.k10), m01 = ldg(fmap + c.k01), m11 = ldg(fmap + c.k11);
-            const T zv = blend(fx, fy, z00, z10, z01, z11);
-            const T mu = blend(fx, fy, m00, m10, m01, m11);
-            const T ax = (z00 - z10) * a.inv_res, ay = (z00 - z01) * a.inv_res;
-            const T q = Mth<T>::rsqrt(ax * ax + ay * ay + (T)1);
-            const T n0 = ax * q, n1 = ay * q, n2 = q;
-            const T dh = Pz - zv;
-            T cw = Mth<T>::contact(dh);
-            if (!ok) cw = (T)0;
-            const T vn = V0 * n0 + V1 * n1 + V2 * n2;
-            const T sp = -(a.stiffness * dh + a.damping * vn);
-            const T tau = tab.driven[slot] * uv + tab.side[slot] * uw;
-            const T e0 = tau * hd[0] - V0, e1 = tau * hd[1] - V1, e2 = tau * hd[2] - V2;
-            const T d0 = mu * e0, d1 = mu * e1, d2 = mu * e2;
-            const T dn = d0 * n0 + d1 * n1 + d2 * n2;
+            const T drv = tab.driven[slot], side = tab.side[slot];
+            PointEval<T> e;
+            eval_point(e, f, px, py, pz, drv, side, ok, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
+            const T n0 = e.rec[4], n1 = e.rec[5], n2 = e.rec[6];
+            const T fx = e.fx, fy = e.fy;
 
             const T Gb0 = nrm[j][0], Gb1 = nrm[j][1], Gb2 = nrm[j][2];
-            const T f = sp * cw * invC;
+            const T fo = e.sp * e.cw * invC;
             const T f_b = Gb0 * n0 + Gb1 * n1 + Gb2 * n2;
-            T nb0 = f * Gb0, nb1 = f * Gb1, nb2 = f * Gb2;
+            T nb0 = fo * Gb0, nb1 = fo * Gb1, nb2 = fo * Gb2;
             const T sc_b = f_b * invC;
-            const T sp_b = sc_b * cw;
-            const T cw_b = sc_b * sp + C_b;
+            const T sp_b = sc_b * e.cw;
+            const T cw_b = sc_b * e.sp + C_b;
             // slip = d - dn n ; dn = d . n
             const T sb0 = slip[j][0], sb1 = slip[j][1], sb2 = slip[j][2];
             const T dn_b = -(sb0 * n0 + sb1 * n1 + sb2 * n2);
-            nb0 += -dn * sb0 + dn_b * d0; nb1 += -dn * sb1 + dn_b * d1; nb2 += -dn * sb2 + dn_b * d2;
+            nb0 += -e.dn * sb0 + dn_b * e.d[0]; nb1 += -e.dn * sb1 + dn_b * e.d[1]; nb2 += -e.dn * sb2 + dn_b * e.d[2];
             const T db0 = sb0 + dn_b * n0, db1 = sb1 + dn_b * n1, db2 = sb2 + dn_b * n2;
             // d = mu e ; e = tau hd - V
-            const T mu_b = db0 * e0 + db1 * e1 + db2 * e2;
-            const T eb0 = mu * db0, eb1 = mu * db1, eb2 = mu * db2;
-            const T tau_b = eb0 * hd[0] + eb1 * hd[1] + eb2 * hd[2];
-            acc[18] += tau * eb0; acc[19] += tau * eb1; acc[20] += tau * eb2;
-            acc[21] += tab.driven[slot] * tau_b; acc[22] += tab.side[slot] * tau_b;
+            const T mu_b = db0 * e.e[0] + db1 * e.e[1] + db2 * e.e[2];
+            const T eb0 = e.mu * db0, eb1 = e.mu * db1, eb2 = e.mu * db2;
+            const T tau_b = eb0 * f.hd[0] + eb1 * f.hd[1] + eb2 * f.hd[2];
+            acc[18] += e.tau * eb0; acc[19] += e.tau * eb1; acc[20] += e.tau * eb2;
+            acc[21] += drv * tau_b; acc[22] += side * tau_b;
             T Vb0 = -eb0, Vb1 = -eb1, Vb2 = -eb2;
             // sp = -(k dh + beta vn) ; vn = V . n
             T dh_b = -a.stiffness * sp_b;
             const T vn_b = -a.damping * sp_b;
             Vb0 += vn_b * n0; Vb1 += vn_b * n1; Vb2 += vn_b * n2;
-            nb0 += vn_b * V0; nb1 += vn_b * V1; nb2 += vn_b * V2;
+            nb0 += vn_b * e.V[0]; nb1 += vn_b * e.V[1]; nb2 += vn_b * e.V[2];
             // cw = sigmoid(-10 dh)
-            dh_b += cw_b * ((T)-10 * cw * ((T)1 - cw));
+            dh_b += cw_b * ((T)-10 * e.cw * ((T)1 - e.cw));
             // dh = Pz - zv
             const T zv_b = -dh_b;
-            // n = (ax q, ay q, q),  q = (ax^2 + ay^2 + 1)^(-1/2)
+            // n = (ax q, ay q, q),  q = (ax^2 + ay^2 + 1)^(-1/2),  ax = -cy / res, ay = -cx / res
+            const T q = n2;
+            const T ax = -e.rec[1] * a.inv_res, ay = -e.rec[2] * a.inv_res;
             const T q_b = nb0 * ax + nb1 * ay + nb2;
             const T q3 = q * q * q;
-            const T ax_b = nb0 * q - q_b * ax * q3;
-            const T ay_b = nb1 * q - q_b * ay * q3;
-            // bilinear weights
+            const T ax_b = (nb0 * q - q_b * ax * q3) * a.inv_res;
+            const T ay_b = (nb1 * q - q_b * ay * q3) * a.inv_res;
+            // bilinear weights (height and friction share them)
             const T gx = (T)1 - fx, gy = (T)1 - fy;
-            T z00_b = zv_b * gx * gy + (ax_b + ay_b) * a.inv_res;
-            T z10_b = zv_b * gx * fy - ax_b * a.inv_res;
-            T z01_b = zv_b * fx * gy - ay_b * a.inv_res;
-            T z11_b = zv_b * fx * fy;
-            T fx_b = zv_b * (-gy * z00 - fy * z10 + gy * z01 + fy * z11) + mu_b * (-gy * m00 - fy * m10 + gy * m01 + fy * m11);
-            T fy_b = zv_b * (-gx * z00 + gx * z10 - fx * z01 + fx * z11) + mu_b * (-gx * m00 + gx * m10 - fx * m01 + fx * m11);
-            if (ok) {
-                if (gz) {
-                    atomicAdd(gz + c.k00, z00_b); atomicAdd(gz + c.k10, z10_b);
-                    atomicAdd(gz + c.k01, z01_b); atomicAdd(gz + c.k11, z11_b);
-                }
-                if (gm) {
-                    atomicAdd(gm + c.k00, mu_b * gx * gy); atomicAdd(gm + c.k10, mu_b * gx * fy);
-                    atomicAdd(gm + c.k01, mu_b * fx * gy); atomicAdd(gm + c.k11, mu_b * fx * fy);
+            const T w00 = gx * gy, w10 = gx * fy, w01 = fx * gy, w11 = fx * fy;
+            // d v / d fx = cx + fy cxy ; d v / d fy = cy + fx cxy
+            const T fx_b = zv_b * e.dz_dfx + mu_b * (e.rec[10] + fy * e.rec[11]);
+            const T fy_b = zv_b * (e.rec[1] + fx * e.rec[3]) + mu_b * (e.rec[9] + fx * e.rec[11]);
+            if (ok && gmap) {
+                const T cg[8] = {zv_b * w00 + (ax_b + ay_b), zv_b * w10 - ax_b, zv_b * w01 - ay_b, zv_b * w11,
+                                 mu_b * w00, mu_b * w10, mu_b * w01, mu_b * w11};
+                if (e.cell >= 0) {
+                    const int cur = wc.cell[slot];
+                    if (cur == e.cell) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) wc.acc[k][slot] += cg[k];
+                    } else {
+                        if (cur >= 0) {
+                            T old[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) old[k] = wc.acc[k][slot];
+                            scatter_corners(gmap, on_map_corners(cur, H, W), old);
+                        }
+                        wc.cell[slot] = e.cell;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) wc.acc[k][slot] = cg[k];
+                    }
+                } else {
+                    const T ggx = e.r[0] * a.inv_res + f.ox, ggy = e.r[1] * a.inv_res + f.oy;
+                    scatter_corners(gmap, flat_corners((long long)ggx, (long long)ggy, H, W), cg);
                 }
             }
             // grid coordinate -> world point
@@ -449,6 +467,7 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             T rb2 = arm[j][2] + Pb2 + (Vb0 * s.w[1] - Vb1 * s.w[0]);
             if (!ok) { rb0 = rb1 = rb2 = (T)0; Vb0 = Vb1 = Vb2 = (T)0; }
             const T okf = ok ? (T)1 : (T)0;
+            const T r0 = e.r[0], r1 = e.r[1], r2 = e.r[2];
             acc[0] += okf * Pb0; acc[1] += okf * Pb1; acc[2] += okf * Pb2;
             acc[3] += Vb0; acc[4] += Vb1; acc[5] += Vb2;
             acc[6] += r1 * Vb2 - r2 * Vb1; acc[7] += r2 * Vb0 - r0 * Vb2; acc[8] += r0 * Vb1 - r1 * Vb0;
@@ -468,9 +487,9 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
         {
             T a0, a1, a2;
             if (hd_norm >= (T)1e-6) {
-                const T dot = hd[0] * acc[18] + hd[1] * acc[19] + hd[2] * acc[20];
+                const T dot = f.hd[0] * acc[18] + f.hd[1] * acc[19] + f.hd[2] * acc[20];
                 const T inv = (T)1 / hd_norm;
-                a0 = (acc[18] - hd[0] * dot) * inv; a1 = (acc[19] - hd[1] * dot) * inv; a2 = (acc[20] - hd[2] * dot) * inv;
+                a0 = (acc[18] - f.hd[0] * dot) * inv; a1 = (acc[19] - f.hd[1] * dot) * inv; a2 = (acc[20] - f.hd[2] * dot) * inv;
             } else {
                 a0 = acc[18] * (T)1e6; a1 = acc[19] * (T)1e6; a2 = acc[20] * (T)1e6;
             }
@@ -492,28 +511,48 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
         T zb = xb[2] + (g.g_x0z ? g.g_x0z[b] : (T)0);   // gradient reaching the snapped height
         zb /= (T)a.N;
         T sx = (T)0, sy = (T)0, rr[6] = {0, 0, 0, 0, 0, 0};
+        StepFrame<T> f;
+        make_frame(f, s, (T)0, (T)0, a.d_max, a.res, a.inv_res);
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
             const int slot = j * 32 + lane;
             const bool ok = (j < PPL - 1 || last_valid);
             const T px = tab.px[slot], py = tab.py[slot], pz = tab.pz[slot];
-            const T Px = s.R[0] * px + s.R[1] * py + s.R[2] * pz + s.x[0];
-            const T Py = s.R[3] * px + s.R[4] * py + s.R[5] * pz + s.x[1];
-            T fx, fy;
-            const Cell c = locate(Mth<T>::to_cells(Px, a.d_max, a.res, a.inv_res),
-                                  Mth<T>::to_cells(Py, a.d_max, a.res, a.inv_res), H, W, fx, fy);
-            const T z00 = ldg(zmap + c.k00), z10 = ldg(zmap + c.k10), z01 = ldg(zmap + c.k01), z11 = ldg(zmap + c.k11);
+            PointEval<T> e;
+            eval_point(e, f, px, py, pz, (T)0, (T)0, ok, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
+            const T fx = e.fx, fy = e.fy;
             const T gx = (T)1 - fx, gy = (T)1 - fy;
             if (ok) {
-                if (gz) {
-                    atomicAdd(gz + c.k00, zb * gx * gy); atomicAdd(gz + c.k10, zb * gx * fy);
-                    atomicAdd(gz + c.k01, zb * fx * gy); atomicAdd(gz + c.k11, zb * fx * fy);
+                if (gmap) {
+                    Corners c;
+                    if (e.cell >= 0) {
+                        c = on_map_corners(e.cell, H, W);
+                    } else {
+                        const T ggx = e.r[0] * a.inv_res + f.ox, ggy = e.r[1] * a.inv_res + f.oy;
+                        c = flat_corners((long long)ggx, (long long)ggy, H, W);
+                    }
+                    const T cg[8] = {zb * gx * gy, zb * gx * fy, zb * fx * gy, zb * fx * fy, (T)0, (T)0, (T)0, (T)0};
+                    scatter_corners(gmap, c, cg);
                 }
-                const T Pb0 = zb * (-gy * z00 - fy * z10 + gy * z01 + fy * z11) * a.inv_res;
-                const T Pb1 = zb * (-gx * z00 + gx * z10 - fx * z01 + fx * z11) * a.inv_res;
+                const T Pb0 = zb * e.dz_dfx * a.inv_res;
+                const T Pb1 = zb * (e.rec[1] + fx * e.rec[3]) * a.inv_res;
                 sx += Pb0; sy += Pb1;
                 rr[0] += Pb0 * px; rr[1] += Pb0 * py; rr[2] += Pb0 * pz;
                 rr[3] += Pb1 * px; rr[4] += Pb1 * py; rr[5] += Pb1 * pz;
+            }
+        }
+        if (gmap) {
+            // drain the lane-private accumulators
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) {
+                const int slot = j * 32 + lane;
+                const int cur = wc.cell[slot];
+                if (cur >= 0) {
+                    T old[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) old[k] = wc.acc[k][slot];
+                    scatter_corners(gmap, on_map_corners(cur, H, W), old);
+                }
             }
         }
         sx = warp_sum(sx); sy = warp_sum(sy);

@@ -15,8 +15,10 @@ struct AdjointArgs {
     const T* g_Ff;       // (B,T,N,3)
     const T* g_x0z;      // (B,)
     // outgoing gradients (nullptr == not wanted)
-    T* g_z;              // (B|1,H,W) accumulated with atomics
-    T* g_mu;             // (B|1,H,W) accumulated with atomics
+    T* g_maps;           // (B|1,H,W,2) zero-initialised scratch: (d/dz, d/dfriction) interleaved per cell, accumulated
+                         // with vector atomics; scatter_map_grads_kernel adds it into the caller's g_z_grid / g_friction.
+                         // nullptr == no map gradient wanted
+    long long g_maps_stride;   // elements between two trajectories' scratch maps (0 = shared)
     T* g_controls;       // (B,T,2)
     T* g_x0;             // (B,3)
     T* g_xd0;            // (B,3)

@@ -36,6 +36,8 @@ struct RolloutArgs {
     const T* pts;                // (N,3) body-frame contact points
     const int* part;             // (N,) driving part id or -1
     const T* ts;                 // (T,) solver time grid (odeint variant only)
+    const T* cells;              // (n_maps, H, W, 12) packed cell table built by build_cell_table (workspace)
+    long long cell_stride;       // elements between two trajectories' tables, 0 = shared
     // outputs
     T* Xs;                       // (B,T,3)
     T* Xds;                      // (B,T,3)
@@ -91,49 +93,103 @@ __device__ __forceinline__ T warp_sum(T v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// grid sampling (dphysics.py:385-455)
+// grid sampling (dphysics.py:385-455) through a packed per-cell table
 // ------------------------------------------------------------------------------------------
-struct Cell {
+// The reference samples  v(fx,fy) = (1-fx)(1-fy) v00 + (1-fx) fy v10 + fx (1-fy) v01 + fx fy v11
+// with v10 the x+1 ("front") and v01 the y+1 ("left") neighbour (weights swapped w.r.t. true
+// bilinear, dphysics.py:442-445) and a normal n = normalize(-(v10-v00)/res, -(v01-v00)/res, 1)
+// that is constant per cell.  Per cell (ix, iy) we therefore pre-compute once per launch
+//   c0 = v00, cy = v10 - v00, cx = v01 - v00, cxy = v00 - v10 - v01 + v11   (height and friction)
+//   n  = the cell normal
+// so that  v = c0 + fy cy + fx (cx + fy cxy)  is 3 FMAs and one contact point costs three
+// 16-byte loads from one 48-byte record instead of eight scattered 4-byte gathers.
+// The neighbour indices use the reference's flat clamp (no per-axis clamp, :432-435).
+constexpr int kCellRec = 12;     // scalars per cell record: c0 cy cx cxy | n0 n1 n2 pad | m0 my mx mxy
+
+struct Corners {
     int k00, k10, k01, k11;      // flat indices: centre, x+1 ("front"), y+1 ("left"), both
 };
 
-// Flat indices of the four neighbours with the reference's flat clamp.  Fast path when the
-// cell is interior (no clamp can trigger); otherwise 64-bit arithmetic like torch's int64.
-template <typename T>
-__device__ __forceinline__ Cell locate(T gx, T gy, int H, int W, T& fx, T& fy) {
-    const int ix = (int)gx;                      // truncation toward zero == .long()
-    const int iy = (int)gy;
-    fx = gx - (T)ix;
-    fy = gy - (T)iy;
-    Cell c;
-    c.k00 = iy + H * ix;
-    c.k10 = c.k00 + H;
-    c.k01 = c.k00 + 1;
-    c.k11 = c.k10 + 1;
-    const bool interior = ((unsigned)ix < (unsigned)(H - 1)) && ((unsigned)iy < (unsigned)(W - 1));
-    if (!interior) {
-        const long long lx = (long long)gx, ly = (long long)gy;
-        fx = gx - (T)lx;
-        fy = gy - (T)ly;
-        const long long last = (long long)H * W - 1;
-        auto cl = [last](long long v) { return (int)(v < 0 ? 0 : (v > last ? last : v)); };
-        c.k00 = cl(ly + (long long)H * lx);
-        c.k10 = cl(ly + (long long)H * (lx + 1));
-        c.k01 = cl((ly + 1) + (long long)H * lx);
-        c.k11 = cl((ly + 1) + (long long)H * (lx + 1));
-    }
+__device__ __forceinline__ Corners flat_corners(long long lx, long long ly, int H, int W) {
+    const long long last = (long long)H * W - 1;
+    auto cl = [last](long long v) { return (int)(v < 0 ? 0 : (v > last ? last : v)); };
+    Corners c;
+    c.k00 = cl(ly + (long long)H * lx);
+    c.k10 = cl(ly + (long long)H * (lx + 1));
+    c.k01 = cl((ly + 1) + (long long)H * lx);
+    c.k11 = cl((ly + 1) + (long long)H * (lx + 1));
+    return c;
+}
+
+// on-map cells (0 <= ix < H, 0 <= iy < W, H == W): only the upper clamp can trigger
+__device__ __forceinline__ Corners on_map_corners(int cell, int H, int W) {
+    const int last = H * W - 1;
+    Corners c;
+    c.k00 = cell;
+    c.k10 = min(cell + H, last);
+    c.k01 = min(cell + 1, last);
+    c.k11 = min(cell + H + 1, last);
     return c;
 }
 
 template <typename T>
-__device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+__device__ __forceinline__ void make_cell_record(const T* __restrict__ z, const T* __restrict__ mu, const Corners& c,
+                                                 T inv_res, T* rec) {
+    const T z00 = z[c.k00], z10 = z[c.k10], z01 = z[c.k01], z11 = z[c.k11];
+    const T m00 = mu[c.k00], m10 = mu[c.k10], m01 = mu[c.k01], m11 = mu[c.k11];
+    rec[0] = z00; rec[1] = z10 - z00; rec[2] = z01 - z00; rec[3] = (z00 - z10) - (z01 - z11);
+    const T ax = (z00 - z10) * inv_res, ay = (z00 - z01) * inv_res;
+    const T q = (T)1 / Mth<T>::sqrt_rn(ax * ax + ay * ay + (T)1);
+    rec[4] = ax * q; rec[5] = ay * q; rec[6] = q; rec[7] = (T)0;
+    rec[8] = m00; rec[9] = m10 - m00; rec[10] = m01 - m00; rec[11] = (m00 - m10) - (m01 - m11);
+}
 
-// value = (1-fx)(1-fy) v00 + (1-fx) fy v10 + fx (1-fy) v01 + fx fy v11   (weights as in the
-// reference: the x+1 neighbour carries the y weight and vice versa, dphysics.py:442-445)
+// one thread per cell of every map
 template <typename T>
-__device__ __forceinline__ T blend(T fx, T fy, T v00, T v10, T v01, T v11) {
-    const T gx = (T)1 - fx, gy = (T)1 - fy;
-    return gx * gy * v00 + gx * fy * v10 + fx * gy * v01 + fx * fy * v11;
+__global__ void build_cell_table_kernel(const T* __restrict__ z, const T* __restrict__ mu, T* __restrict__ cells,
+                                        int n_maps, int H, int W, long long map_stride, T inv_res) {
+    const long long total = (long long)n_maps * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / ((long long)H * W));
+        const int k = (int)(i - (long long)m * H * W);
+        const int ix = k / W, iy = k - ix * W;
+        const Corners c = flat_corners(ix, iy, H, W);
+        T rec[kCellRec];
+        make_cell_record(z + m * map_stride, mu + m * map_stride, c, inv_res, rec);
+        T* out = cells + i * kCellRec;
+#pragma unroll
+        for (int j = 0; j < kCellRec; ++j) out[j] = rec[j];
+    }
+}
+
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { using type = float4; static constexpr int n = 4; };
+template <> struct Vec16<double> { using type = double2; static constexpr int n = 2; };
+
+// 16-byte vector loads of one record (read-only path)
+template <typename T>
+__device__ __forceinline__ void load_cell_record(const T* __restrict__ p, T* rec) {
+    using V = typename Vec16<T>::type;
+    constexpr int n = Vec16<T>::n;
+    const V* q = reinterpret_cast<const V*>(p);
+#pragma unroll
+    for (int i = 0; i < kCellRec / n; ++i) {
+        const V v = __ldg(q + i);
+        const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+        for (int j = 0; j < n; ++j) rec[i * n + j] = e[j];
+    }
+}
+
+// points outside [0,H) x [0,W): the reference's clamped flat indices, straight from the raw maps (rare)
+template <typename T>
+__device__ __noinline__ void sample_off_map(const T* __restrict__ z, const T* __restrict__ mu, T gx, T gy, int H, int W,
+                                            T inv_res, T* out /* [kCellRec + 2] */) {
+    const long long lx = (long long)gx, ly = (long long)gy;
+    out[kCellRec + 0] = gx - (T)lx;
+    out[kCellRec + 1] = gy - (T)ly;
+    const Corners c = flat_corners(lx, ly, H, W);
+    make_cell_record(z, mu, c, inv_res, out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -179,6 +235,96 @@ __device__ __forceinline__ void rodrigues_right(T* R, const T* w, T dt) {
             Rn[r * 3 + c] = R[r * 3 + 0] * E[0 * 3 + c] + R[r * 3 + 1] * E[1 * 3 + c] + R[r * 3 + 2] * E[2 * 3 + c];
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = Rn[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// phase 1 of a step for one contact point (shared by the forward and the adjoint kernels)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct StepFrame {          // warp-uniform quantities of the current step
+    T R[9], x[3], v[3], w[3];
+    T ox, oy;               // (x + d_max) / res : grid offset of the body origin
+    T hd[3];                // thrust direction: first column of R, normalised (dphysics.py:237)
+    T uv, uw;               // controls (v, w)
+};
+
+template <typename T>
+__device__ __forceinline__ void make_frame(StepFrame<T>& f, const Body<T>& s, T uv, T uw, const T d_max, const T res,
+                                           const T inv_res) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f.R[i] = s.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { f.x[i] = s.x[i]; f.v[i] = s.v[i]; f.w[i] = s.w[i]; }
+    f.ox = Mth<T>::to_cells(s.x[0], d_max, res, inv_res);
+    f.oy = Mth<T>::to_cells(s.x[1], d_max, res, inv_res);
+    const T nn = Mth<T>::sqrt_rn(s.R[0] * s.R[0] + s.R[3] * s.R[3] + s.R[6] * s.R[6]);
+    const T inv = (T)1 / Mth<T>::fmax_(nn, (T)1e-6);
+    f.hd[0] = s.R[0] * inv; f.hd[1] = s.R[3] * inv; f.hd[2] = s.R[6] * inv;
+    f.uv = uv; f.uw = uw;
+}
+
+template <typename T>
+struct PointEval {
+    T r[3];                 // lever arm R p (== P - x)
+    T V[3];                 // point velocity v + w x r
+    T rec[kCellRec];        // cell record (coefficients, normal)
+    T fx, fy;               // position inside the cell
+    T dz_dfx;               // d zv / d fx = cx + fy cxy
+    T mu, dh, cw, vn, sp;   // friction coef., height above terrain, soft-contact weight, normal speed, -(k dh + b vn)
+    T tau;                  // commanded track speed at the point
+    T e[3], d[3], dn;       // slip: e = tau hd - V, d = mu e, dn = d . n
+    T sl[3];                // tangential slip d - dn n
+    int cell;               // index into the cell table, -1 when the point is off the map
+};
+
+// `cells` / `zmap` / `fmap` are already offset to this trajectory's map.
+template <typename T>
+__device__ __forceinline__ void eval_point(PointEval<T>& o, const StepFrame<T>& f, T px, T py, T pz, T drv, T side,
+                                           bool valid, const T* __restrict__ cells, const T* __restrict__ zmap,
+                                           const T* __restrict__ fmap, int H, int W, T inv_res, T stiffness, T damping) {
+    // r = R p ; V = v + w x r                                                  dphysics.py:200-204
+    o.r[0] = f.R[0] * px + f.R[1] * py + f.R[2] * pz;
+    o.r[1] = f.R[3] * px + f.R[4] * py + f.R[5] * pz;
+    o.r[2] = f.R[6] * px + f.R[7] * py + f.R[8] * pz;
+    o.V[0] = f.v[0] + (f.w[1] * o.r[2] - f.w[2] * o.r[1]);
+    o.V[1] = f.v[1] + (f.w[2] * o.r[0] - f.w[0] * o.r[2]);
+    o.V[2] = f.v[2] + (f.w[0] * o.r[1] - f.w[1] * o.r[0]);
+    // grid coordinates of P = r + x and the cell they fall in                  dphysics.py:419-424
+    const T gx = o.r[0] * inv_res + f.ox;
+    const T gy = o.r[1] * inv_res + f.oy;
+    const int ix = (int)gx, iy = (int)gy;        // truncation toward zero == .long()
+    const bool on_map = ((unsigned)ix < (unsigned)H) && ((unsigned)iy < (unsigned)W);
+    o.fx = gx - (T)ix;
+    o.fy = gy - (T)iy;
+    // the record load is unconditional (cell 0 stands in for off-map points) so that the loads of all
+    // the lane's points can be in flight together; off-map points are patched afterwards (rare)
+    const int cell = on_map ? ix * W + iy : 0;
+    load_cell_record(cells + (long long)cell * kCellRec, o.rec);
+    o.cell = on_map ? cell : -1;
+    if (!on_map) {
+        // the record goes through a local buffer so that o.rec itself stays in registers
+        T tmp[kCellRec + 2];
+        sample_off_map(zmap, fmap, gx, gy, H, W, inv_res, tmp);
+#pragma unroll
+        for (int k = 0; k < kCellRec; ++k) o.rec[k] = tmp[k];
+        o.fx = tmp[kCellRec]; o.fy = tmp[kCellRec + 1];
+    }
+    // height, friction, normal                                                 dphysics.py:211-216
+    o.dz_dfx = o.rec[2] + o.fy * o.rec[3];
+    const T zv = o.rec[0] + o.fy * o.rec[1] + o.fx * o.dz_dfx;
+    o.mu = o.rec[8] + o.fy * o.rec[9] + o.fx * (o.rec[10] + o.fy * o.rec[11]);
+    const T n0 = o.rec[4], n1 = o.rec[5], n2 = o.rec[6];
+    // soft contact, spring-damper magnitude                                    dphysics.py:220-232
+    o.dh = (o.r[2] + f.x[2]) - zv;
+    o.cw = valid ? Mth<T>::contact(o.dh) : (T)0;
+    o.vn = o.V[0] * n0 + o.V[1] * n1 + o.V[2] * n2;
+    o.sp = -(stiffness * o.dh + damping * o.vn);
+    // tangential slip w.r.t. the commanded track speed                         dphysics.py:237-249
+    o.tau = drv * f.uv + side * f.uw;
+    o.e[0] = o.tau * f.hd[0] - o.V[0]; o.e[1] = o.tau * f.hd[1] - o.V[1]; o.e[2] = o.tau * f.hd[2] - o.V[2];
+    o.d[0] = o.mu * o.e[0]; o.d[1] = o.mu * o.e[1]; o.d[2] = o.mu * o.e[2];
+    o.dn = o.d[0] * n0 + o.d[1] * n1 + o.d[2] * n2;
+    o.sl[0] = o.d[0] - o.dn * n0; o.sl[1] = o.d[1] - o.dn * n1; o.sl[2] = o.d[2] - o.dn * n2;
 }
 
 // Body points staged once per block: slot = j*32 + lane == point index.  Padded slots (only in

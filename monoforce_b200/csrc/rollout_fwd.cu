@@ -13,18 +13,27 @@ template <typename T, int PPL, int VARIANT>
 static LaunchError launch_ppl(const RolloutArgs<T>& a, cudaStream_t st) {
     const dim3 grid((a.B + kFwdWarps - 1) / kFwdWarps), block(kFwdWarps * 32);
     const bool forces = a.Fs != nullptr, cost = a.cost != nullptr;
+    if (forces && ((((uintptr_t)a.Fs) | ((uintptr_t)a.Ff)) & 15))
+        return {"F_springs / F_frictions must be 16-byte aligned (rows leave the SM as TMA bulk stores)"};
+    const size_t smem = forces ? RowStage<T>::smem_bytes(a.N, kFwdWarps) : 0;
+    auto go = [&](auto kern) -> LaunchError {
+        // static (point table) + dynamic (row images) can exceed the 48 KB default: always opt in
+        if (smem > 0 &&
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return {"cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"};
+        kern<<<grid, block, smem, st>>>(a);
+        count_launch();
+        return {nullptr};
+    };
     if (VARIANT == kOdeintEuler) {
         if (cost) return {"cost output is defined for the step-loop variant only"};
-        if (forces) rollout_fwd_kernel<T, PPL, VARIANT, true, false><<<grid, block, 0, st>>>(a);
-        else        rollout_fwd_kernel<T, PPL, VARIANT, false, false><<<grid, block, 0, st>>>(a);
-    } else {
-        if (forces && cost)       rollout_fwd_kernel<T, PPL, VARIANT, true, true><<<grid, block, 0, st>>>(a);
-        else if (forces)          rollout_fwd_kernel<T, PPL, VARIANT, true, false><<<grid, block, 0, st>>>(a);
-        else if (cost)            rollout_fwd_kernel<T, PPL, VARIANT, false, true><<<grid, block, 0, st>>>(a);
-        else                      rollout_fwd_kernel<T, PPL, VARIANT, false, false><<<grid, block, 0, st>>>(a);
+        if (forces) return go(rollout_fwd_kernel<T, PPL, VARIANT, true, false>);
+        return go(rollout_fwd_kernel<T, PPL, VARIANT, false, false>);
     }
-    count_launch();
-    return {nullptr};
+    if (forces && cost) return go(rollout_fwd_kernel<T, PPL, VARIANT, true, true>);
+    if (forces) return go(rollout_fwd_kernel<T, PPL, VARIANT, true, false>);
+    if (cost) return go(rollout_fwd_kernel<T, PPL, VARIANT, false, true>);
+    return go(rollout_fwd_kernel<T, PPL, VARIANT, false, false>);
 }
 
 template <>

@@ -17,8 +17,52 @@ namespace mfb {
 
 constexpr int kFwdWarps = 4;   // trajectories per CTA
 
+// Force rows leave the SM through TMA bulk stores: every lane drops its points' forces into a
+// per-warp shared-memory image of the (N,3) row (stride-3 words across lanes: conflict free), the
+// 16-byte aligned interior of the row then goes out as ONE cp.async.bulk per tensor and step, the
+// <= 3 leading / trailing scalars with plain stores.  A row of N*3 scalars starts at an arbitrary
+// 4-byte (8-byte) phase in global memory, so its shared image is placed at the same phase.
+template <typename T> struct RowStage {
+    static constexpr int kPer16 = 16 / (int)sizeof(T);            // scalars per 16 bytes
+    __host__ __device__ static int stride(int N) { return (N * 3 + 2 * kPer16 + kPer16 - 1) / kPer16 * kPer16; }
+    __host__ static size_t smem_bytes(int N, int warps) { return (size_t)warps * 2 * stride(N) * sizeof(T); }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Emits the two staged rows (same phase): `img_*` are 16-byte aligned shared buffers, rows sit at img + phase.
+template <typename T>
+__device__ __forceinline__ void emit_rows(T* __restrict__ grow_s, T* __restrict__ grow_f, const T* img_s, const T* img_f,
+                                          int phase, int n, int lane) {
+    constexpr int P = RowStage<T>::kPer16;
+    const int head = (P - phase) & (P - 1);                 // scalars before the first 16-byte boundary
+    const int body = (n - head) & ~(P - 1);                 // scalars in the aligned interior
+    const int tail = n - head - body;
+    if (lane == 0) {
+        if (body > 0) bulk_store(grow_s + head, img_s + phase + head, (uint32_t)(body * sizeof(T)));
+        if (body > 0) bulk_store(grow_f + head, img_f + phase + head, (uint32_t)(body * sizeof(T)));
+        bulk_commit();
+    }
+    // lanes 8..8+head-1 write the head scalars, lanes 16..16+tail-1 the tail scalars (at most 3 each)
+    const int hk = lane - 8, tk = lane - 16;
+    if ((unsigned)hk < (unsigned)head) { grow_s[hk] = img_s[phase + hk]; grow_f[hk] = img_f[phase + hk]; }
+    if ((unsigned)tk < (unsigned)tail) {
+        const int o = head + body + tk;
+        grow_s[o] = img_s[phase + o]; grow_f[o] = img_f[phase + o];
+    }
+}
+
 template <typename T, int PPL, int VARIANT, bool FORCES, bool COST>
-__global__ void __launch_bounds__(kFwdWarps * 32)
+__global__ void __launch_bounds__(kFwdWarps * 32, (sizeof(T) == 4 && PPL <= 7) ? 4 : 1)
 rollout_fwd_kernel(const RolloutArgs<T> a) {
     __shared__ PointTable<T> tab;
     fill_point_table(tab, a, PPL * 32);
@@ -30,8 +74,14 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
     const int n_last = a.N - (PPL - 1) * 32;            // valid lanes of the last slot
     const bool last_valid = lane < n_last;
 
+    extern __shared__ __align__(16) unsigned char stage_raw[];
+    const int row_stride = RowStage<T>::stride(a.N);
+    T* const img_s = reinterpret_cast<T*>(stage_raw) + (size_t)(threadIdx.x >> 5) * 2 * row_stride;   // F_spring row image
+    T* const img_f = img_s + row_stride;                                                                 // F_friction row image
+
     const T* __restrict__ zmap = a.z + (long long)b * a.map_stride;
     const T* __restrict__ fmap = a.mu + (long long)b * a.map_stride;
+    const T* __restrict__ cells = a.cells + (long long)b * a.cell_stride;
     const T* __restrict__ ctrl = a.controls + (long long)b * a.nT * 2;
     const int H = a.H, W = a.W;
 
@@ -40,19 +90,17 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
 
     // ---- start-height snap: x.z = mean_p interp(z, (R p + x).xy)            dphysics.py:567-571
     {
+        StepFrame<T> f;
+        make_frame(f, s, (T)0, (T)0, a.d_max, a.res, a.inv_res);
         T acc = (T)0;
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
             const int slot = j * 32 + lane;
-            const T px = tab.px[slot], py = tab.py[slot], pz = tab.pz[slot];
-            const T Px = s.R[0] * px + s.R[1] * py + s.R[2] * pz + s.x[0];
-            const T Py = s.R[3] * px + s.R[4] * py + s.R[5] * pz + s.x[1];
-            T fx, fy;
-            const Cell c = locate(Mth<T>::to_cells(Px, a.d_max, a.res, a.inv_res),
-                                  Mth<T>::to_cells(Py, a.d_max, a.res, a.inv_res), H, W, fx, fy);
-            T zv = blend(fx, fy, ldg(zmap + c.k00), ldg(zmap + c.k10), ldg(zmap + c.k01), ldg(zmap + c.k11));
-            if (j == PPL - 1 && !last_valid) zv = (T)0;
-            acc += zv;
+            PointEval<T> e;
+            eval_point(e, f, tab.px[slot], tab.py[slot], tab.pz[slot], (T)0, (T)0, true, cells, zmap, fmap, H, W,
+                       a.inv_res, a.stiffness, a.damping);
+            const T zv = e.rec[0] + e.fy * e.rec[1] + e.fx * e.dz_dfx;
+            acc += (j == PPL - 1 && !last_valid) ? (T)0 : zv;
         }
         acc = warp_sum(acc);
         s.x[2] = acc / (T)a.N;
@@ -111,13 +159,8 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
         T uv_n = uv, uw_n = uw;
         if (t + 1 < a.nT) { uv_n = ctrl[(t + 1) * 2]; uw_n = ctrl[(t + 1) * 2 + 1]; }
 
-        // thrust direction: first column of R, normalised                       dphysics.py:237
-        T hd[3];
-        {
-            const T nn = Mth<T>::sqrt_rn(s.R[0] * s.R[0] + s.R[3] * s.R[3] + s.R[6] * s.R[6]);
-            const T inv = (T)1 / Mth<T>::fmax_(nn, (T)1e-6);
-            hd[0] = s.R[0] * inv; hd[1] = s.R[3] * inv; hd[2] = s.R[6] * inv;
-        }
+        StepFrame<T> f;
+        make_frame(f, s, uv, uw, a.d_max, a.res, a.inv_res);
 
         T nrm[PPL][3], sc[PPL], slip[PPL][3], arm[PPL][3];
         T C = (T)0;
@@ -125,55 +168,35 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
             const int slot = j * 32 + lane;
-            const T px = tab.px[slot], py = tab.py[slot], pz = tab.pz[slot];
-            // r = R p ; P = r + x ; Pd = v + w x r                              dphysics.py:200-204
-            const T r0 = s.R[0] * px + s.R[1] * py + s.R[2] * pz;
-            const T r1 = s.R[3] * px + s.R[4] * py + s.R[5] * pz;
-            const T r2 = s.R[6] * px + s.R[7] * py + s.R[8] * pz;
-            const T Px = r0 + s.x[0], Py = r1 + s.x[1], Pz = r2 + s.x[2];
-            const T V0 = s.v[0] + (s.w[1] * r2 - s.w[2] * r1);
-            const T V1 = s.v[1] + (s.w[2] * r0 - s.w[0] * r2);
-            const T V2 = s.v[2] + (s.w[0] * r1 - s.w[1] * r0);
-            // terrain height, normal, friction at the point                     dphysics.py:211-216
-            T fx, fy;
-            const Cell c = locate(Mth<T>::to_cells(Px, a.d_max, a.res, a.inv_res),
-                                  Mth<T>::to_cells(Py, a.d_max, a.res, a.inv_res), H, W, fx, fy);
-            const T z00 = ldg(zmap + c.k00), z10 = ldg(zmap + c.k10), z01 = ldg(zmap + c.k01), z11 = ldg(zmap + c.k11);
-            const T m00 = ldg(fmap + c.k00), m10 = ldg(fmap + c.k10), m01 = ldg(fmap + c.k01), m11 = ldg(fmap + c.k11);
-            const T zv = blend(fx, fy, z00, z10, z01, z11);
-            const T mu = blend(fx, fy, m00, m10, m01, m11);
-            const T ax = (z00 - z10) * a.inv_res;       // -dz/dx
-            const T ay = (z00 - z01) * a.inv_res;       // -dz/dy
-            const T inv_n = Mth<T>::rsqrt(ax * ax + ay * ay + (T)1);
-            const T n0 = ax * inv_n, n1 = ay * inv_n, n2 = inv_n;
-            // soft contact + spring-damper magnitude                            dphysics.py:220-232
-            const T dh = Pz - zv;
-            T cw = Mth<T>::contact(dh);
-            if (j == PPL - 1 && !last_valid) cw = (T)0;
-            C += cw;
-            const T vn = V0 * n0 + V1 * n1 + V2 * n2;
-            sc[j] = -(a.stiffness * dh + a.damping * vn) * cw;
-            // tangential slip of the driven point w.r.t. the commanded track speed   dphysics.py:237-249
-            const T tau = tab.driven[slot] * uv + tab.side[slot] * uw;
-            const T d0 = mu * (tau * hd[0] - V0), d1 = mu * (tau * hd[1] - V1), d2 = mu * (tau * hd[2] - V2);
-            const T dn = d0 * n0 + d1 * n1 + d2 * n2;
-            slip[j][0] = d0 - dn * n0; slip[j][1] = d1 - dn * n1; slip[j][2] = d2 - dn * n2;
-            nrm[j][0] = n0; nrm[j][1] = n1; nrm[j][2] = n2;
-            arm[j][0] = r0; arm[j][1] = r1; arm[j][2] = r2;
+            PointEval<T> e;
+            eval_point(e, f, tab.px[slot], tab.py[slot], tab.pz[slot], tab.driven[slot], tab.side[slot],
+                       (j < PPL - 1) || last_valid, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
+            C += e.cw;
+            sc[j] = e.sp * e.cw;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { slip[j][k] = e.sl[k]; nrm[j][k] = e.rec[4 + k]; arm[j][k] = e.r[k]; }
         }
 
         C = warp_sum(C);
         const T invC = Mth<T>::rcp(C);
 
-        T sum[9];
+        T sum[6];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) sum[k] = (T)0;
+        for (int k = 0; k < 6; ++k) sum[k] = (T)0;
         T nf_sum = (T)0, nf_sq = (T)0;
         T h = (T)0;
         if (VARIANT == kOdeintEuler) h = a.ts[t + 1] - a.ts[t];
 
         T* __restrict__ Fs_t = FORCES ? Fs_b + (long long)(VARIANT == kOdeintEuler ? t + 1 : t) * rowF : nullptr;
         T* __restrict__ Ff_t = FORCES ? Ff_b + (long long)(VARIANT == kOdeintEuler ? t + 1 : t) * rowF : nullptr;
+        // phase of the row start inside a 16-byte line (both tensors share it: same shape, 16-byte aligned bases)
+        const int phase = FORCES ? (int)((((long long)b * a.nT + (VARIANT == kOdeintEuler ? t + 1 : t)) * rowF) &
+                                         (RowStage<T>::kPer16 - 1)) : 0;
+        if (FORCES) {
+            // the previous step's bulk stores must have finished READING the row images
+            if (lane == 0) bulk_wait_read();
+            __syncwarp();
+        }
 
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
@@ -182,29 +205,34 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
             const T Nf = Mth<T>::sqrt(Fr0 * Fr0 + Fr1 * Fr1 + Fr2 * Fr2);                   // dphysics.py:238
             const T Ft0 = clampT(Nf * slip[j][0], a.mg), Ft1 = clampT(Nf * slip[j][1], a.mg), Ft2 = clampT(Nf * slip[j][2], a.mg);
             const T F0 = Fr0 + Ft0, F1 = Fr1 + Ft1, F2 = Fr2 + Ft2;
-            sum[0] += Fr0; sum[1] += Fr1; sum[2] += Fr2;
-            sum[3] += Ft0; sum[4] += Ft1; sum[5] += Ft2;
-            sum[6] += arm[j][1] * F2 - arm[j][2] * F1;                                       // dphysics.py:255
-            sum[7] += arm[j][2] * F0 - arm[j][0] * F2;
-            sum[8] += arm[j][0] * F1 - arm[j][1] * F0;
+            sum[0] += F0; sum[1] += F1; sum[2] += F2;                                        // dphysics.py:265 (F_spring + F_friction)
+            sum[3] += arm[j][1] * F2 - arm[j][2] * F1;                                       // dphysics.py:255
+            sum[4] += arm[j][2] * F0 - arm[j][0] * F2;
+            sum[5] += arm[j][0] * F1 - arm[j][1] * F0;
             if (COST) { nf_sum += Nf; nf_sq += Nf * Nf; }
             if (FORCES) {
                 if (j < PPL - 1 || last_valid) {
-                    const long long o = (long long)(j * 32 + lane) * 3;
+                    const int o = phase + (j * 32 + lane) * 3;
                     if (VARIANT == kOdeintEuler) {
                         accF[j][0] += h * Fr0; accF[j][1] += h * Fr1; accF[j][2] += h * Fr2;
                         accF[j][3] += h * Ft0; accF[j][4] += h * Ft1; accF[j][5] += h * Ft2;
-                        Fs_t[o + 0] = accF[j][0]; Fs_t[o + 1] = accF[j][1]; Fs_t[o + 2] = accF[j][2];
-                        Ff_t[o + 0] = accF[j][3]; Ff_t[o + 1] = accF[j][4]; Ff_t[o + 2] = accF[j][5];
+                        img_s[o + 0] = accF[j][0]; img_s[o + 1] = accF[j][1]; img_s[o + 2] = accF[j][2];
+                        img_f[o + 0] = accF[j][3]; img_f[o + 1] = accF[j][4]; img_f[o + 2] = accF[j][5];
                     } else {
-                        Fs_t[o + 0] = Fr0; Fs_t[o + 1] = Fr1; Fs_t[o + 2] = Fr2;
-                        Ff_t[o + 0] = Ft0; Ff_t[o + 1] = Ft1; Ff_t[o + 2] = Ft2;
+                        img_s[o + 0] = Fr0; img_s[o + 1] = Fr1; img_s[o + 2] = Fr2;
+                        img_f[o + 0] = Ft0; img_f[o + 1] = Ft1; img_f[o + 2] = Ft2;
                     }
                 }
             }
         }
+        if (FORCES) {
+            // generic-proxy writes -> visible to the async proxy, then one lane launches the two bulk stores
+            fence_async_smem();
+            __syncwarp();
+            emit_rows(Fs_t, Ff_t, img_s, img_f, phase, (int)rowF, lane);
+        }
 #pragma unroll
-        for (int k = 0; k < 9; ++k) sum[k] = warp_sum(sum[k]);
+        for (int k = 0; k < 6; ++k) sum[k] = warp_sum(sum[k]);
 
         if (COST) {
             // unbiased std over the N points of |F_spring|, then Welford over steps
@@ -222,11 +250,11 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
         T wd[3], vd[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            wd[r] = clampT(a.Iinv[r * 3 + 0] * sum[6] + a.Iinv[r * 3 + 1] * sum[7] + a.Iinv[r * 3 + 2] * sum[8], a.omega_max);
+            wd[r] = clampT(a.Iinv[r * 3 + 0] * sum[3] + a.Iinv[r * 3 + 1] * sum[4] + a.Iinv[r * 3 + 2] * sum[5], a.omega_max);
         }
-        vd[0] = ((T)0 + sum[0] + sum[3]) * a.inv_mass;
-        vd[1] = ((T)0 + sum[1] + sum[4]) * a.inv_mass;
-        vd[2] = (-a.mg + sum[2] + sum[5]) * a.inv_mass;
+        vd[0] = sum[0] * a.inv_mass;
+        vd[1] = sum[1] * a.inv_mass;
+        vd[2] = (sum[2] - a.mg) * a.inv_mass;
 
         if (VARIANT == kStepLoop) {
             // semi-implicit Euler                                               dphysics.py:274-288
@@ -260,6 +288,7 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
         uv = uv_n; uw = uw_n;
     }
 
+    if (FORCES && lane == 0) bulk_wait_all();
     if (COST && lane == 0) {
         const int n = n_steps;
         a.cost[b] = n > 1 ? Mth<T>::sqrt_rn(cost_m2 / (T)(n - 1)) : (T)0;

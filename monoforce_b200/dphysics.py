@@ -107,6 +107,13 @@ def _require_cuda(*tensors):
                 f"got a tensor on {t.device}. Construct DPhysics(cfg, device='cuda').")
 
 
+def _workspace(lib, meta, dev):
+    n = int(lib.mfb_rollout_workspace_bytes(C.byref(meta.desc), meta.dtype_code))
+    if n < 0:
+        raise RuntimeError("mfb_rollout_workspace_bytes rejected the rollout description")
+    return torch.empty(n, dtype=torch.uint8, device=dev)
+
+
 class _Rollout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z, mu, controls, x0, xd0, R0, om0, meta: _RolloutMeta):
@@ -123,7 +130,9 @@ class _Rollout(torch.autograd.Function):
         Ff = new(B, T, N, 3) if meta.want_forces else None
         x0z = new(B)
         cost = new(B) if meta.want_cost else None
+        ws = _workspace(lib, meta, dev)
         io = _lib.RolloutBuffers(
+            workspace=_ptr(ws), workspace_bytes=ws.numel(),
             z_grid=_ptr(z), friction=_ptr(mu), controls=_ptr(controls), x0=_ptr(x0), xd0=_ptr(xd0), R0=_ptr(R0),
             omega0=_ptr(om0), points=_ptr(meta.points), part_id=_ptr(meta.part_id), ts=_ptr(meta.ts),
             Xs=_ptr(Xs), Xds=_ptr(Xds), Rs=_ptr(Rs), Omegas=_ptr(Oms), F_springs=_ptr(Fs), F_frictions=_ptr(Ff),
@@ -161,7 +170,9 @@ class _Rollout(torch.autograd.Function):
         g_xd0 = torch.empty_like(xd0) if need[4] else None
         g_R0 = torch.empty_like(R0) if need[5] else None
         g_om0 = torch.empty_like(om0) if need[6] else None
+        ws = _workspace(lib, meta, dev)
         io = _lib.RolloutBuffers(
+            workspace=_ptr(ws), workspace_bytes=ws.numel(),
             z_grid=_ptr(z), friction=_ptr(mu), controls=_ptr(controls), x0=_ptr(x0), xd0=_ptr(xd0), R0=_ptr(R0),
             omega0=_ptr(om0), points=_ptr(meta.points), part_id=_ptr(meta.part_id), ts=_ptr(meta.ts),
             Xs=_ptr(Xs), Xds=_ptr(Xds), Rs=_ptr(Rs), Omegas=_ptr(Oms), F_springs=None, F_frictions=None,

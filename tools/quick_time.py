@@ -44,3 +44,17 @@ print(f"fwd+bwd (forces materialised): best {best:.3f} ms mean {mean:.3f} ms -> 
 sim.return_forces = False
 best, mean = timed(fb)
 print(f"fwd+bwd (no forces): best {best:.3f} ms mean {mean:.3f} ms -> {B*T/best*1e3:.3e} steps/s")
+ck = controls.clone().requires_grad_(True)
+def fb_ctrl():
+    ck.grad = None
+    (Xs, _, _, _), _ = sim(z.unsqueeze(0), ck)
+    Xs.pow(2).mean().backward()
+best, mean = timed(fb_ctrl)
+print(f"fwd+bwd (no forces, grads to controls only = no atomics): best {best:.3f} ms")
+fk = torch.full_like(z, 0.5).requires_grad_(True)
+def fb_both():
+    zk.grad = None; fk.grad = None
+    (Xs, _, _, _), _ = sim(zk.unsqueeze(0), controls, friction=fk.unsqueeze(0))
+    Xs.pow(2).mean().backward()
+best, mean = timed(fb_both)
+print(f"fwd+bwd (no forces, grads to z and friction): best {best:.3f} ms")
