@@ -77,9 +77,9 @@ __device__ __forceinline__ void rodrigues_right_bwd(const T* w, T dt, const T* E
     const T thc = Mth<T>::fmax_(th, (T)1e-6);
     const T inv = (T)1 / thc;
     const T k0 = w[0] * inv, k1 = w[1] * inv, k2 = w[2] * inv;
-    T sn, cs;
-    Mth<T>::sincos(th * dt, &sn, &cs);
-    const T c1 = (T)1 - cs;
+    T sn, c1;
+    sin_versin(th * dt, &sn, &c1);
+    const T cs = (T)1 - c1;
     const T kk = k0 * k0 + k1 * k1 + k2 * k2;
     const T tr = Eb[0] + Eb[4] + Eb[8];
     const T a0 = Eb[7] - Eb[5], a1 = Eb[2] - Eb[6], a2 = Eb[3] - Eb[1];   // axial part of Eb
@@ -224,9 +224,8 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                 const T th = Mth<T>::sqrt_rn(w_post[0] * w_post[0] + w_post[1] * w_post[1] + w_post[2] * w_post[2]);
                 const T inv = (T)1 / Mth<T>::fmax_(th, (T)1e-6);
                 const T k0 = w_post[0] * inv, k1 = w_post[1] * inv, k2 = w_post[2] * inv;
-                T sn, cs;
-                Mth<T>::sincos(th * a.dt, &sn, &cs);
-                const T c1 = (T)1 - cs;
+                T sn, c1;
+                sin_versin(th * a.dt, &sn, &c1);
                 const T kk = k0 * k0 + k1 * k1 + k2 * k2;
                 E[0] = (T)1 + c1 * (k0 * k0 - kk);  E[1] = -sn * k2 + c1 * k0 * k1;     E[2] = sn * k1 + c1 * k0 * k2;
                 E[3] = sn * k2 + c1 * k0 * k1;      E[4] = (T)1 + c1 * (k1 * k1 - kk);  E[5] = -sn * k0 + c1 * k1 * k2;

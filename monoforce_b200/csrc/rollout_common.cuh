@@ -212,15 +212,30 @@ __device__ __forceinline__ void load_body(Body<T>& s, const RolloutArgs<T>& a, i
     for (int i = 0; i < 9; ++i) s.R[i] = a.R0[b * 9 + i];
 }
 
+// sin(x) and 1 - cos(x).  One integration step turns the body by |w| dt, a small angle: below 0.5 rad
+// an odd/even Taylor pair (error < 1e-10) is both cheaper than libm's sincos and free of the
+// cancellation in 1 - cos(x); larger angles (tumbling states) use libm.
+template <typename T>
+__device__ __forceinline__ void sin_versin(T x, T* sn, T* vs) {
+    if (sizeof(T) == 4 && x < (T)0.5) {       // x = |w| dt >= 0; double precision always takes libm
+        const T x2 = x * x;
+        *sn = x * ((T)1 + x2 * ((T)(-1.0 / 6) + x2 * ((T)(1.0 / 120) + x2 * ((T)(-1.0 / 5040) + x2 * (T)(1.0 / 362880)))));
+        *vs = x2 * ((T)0.5 + x2 * ((T)(-1.0 / 24) + x2 * ((T)(1.0 / 720) + x2 * ((T)(-1.0 / 40320) + x2 * (T)(1.0 / 3628800)))));
+    } else {
+        T cs;
+        Mth<T>::sincos(x, sn, &cs);
+        *vs = (T)1 - cs;
+    }
+}
+
 // R <- R (I + K sin(th dt) + K K (1 - cos(th dt))),  K = [w]x / max(|w|, 1e-6)   (dphysics.py:290-324)
 template <typename T>
 __device__ __forceinline__ void rodrigues_right(T* R, const T* w, T dt) {
     const T th = Mth<T>::sqrt_rn(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
     const T inv = (T)1 / Mth<T>::fmax_(th, (T)1e-6);
     const T k0 = w[0] * inv, k1 = w[1] * inv, k2 = w[2] * inv;
-    T sn, cs;
-    Mth<T>::sincos(th * dt, &sn, &cs);
-    const T c1 = (T)1 - cs;
+    T sn, c1;
+    sin_versin(th * dt, &sn, &c1);
     const T kk = k0 * k0 + k1 * k1 + k2 * k2;
     // E = I + sn K + c1 (k k^T - |k|^2 I)
     T E[9];

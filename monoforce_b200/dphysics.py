@@ -96,7 +96,7 @@ def _ptr(t):
 
 class _RolloutMeta:
     """Everything that is not a differentiable tensor."""
-    __slots__ = ("desc", "points", "part_id", "ts", "want_forces", "want_cost", "dtype_code", "B", "T", "N")
+    __slots__ = ("desc", "points", "part_id", "ts", "want_forces", "want_cost", "dtype_code", "B", "T", "N", "timings")
 
 
 def _require_cuda(*tensors):
@@ -105,6 +105,16 @@ def _require_cuda(*tensors):
             raise RuntimeError(
                 "monoforce_b200.DPhysics runs on CUDA only (sm_100a kernels, no CPU fallback); "
                 f"got a tensor on {t.device}. Construct DPhysics(cfg, device='cuda').")
+
+
+def _events(meta, name):
+    """CUDA events bracketing exactly the library call on the launching stream (DPhysics.timings opt-in)."""
+    if meta.timings is None:
+        return None
+    ev = (name, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev[1].record()
+    meta.timings.append(ev)
+    return ev
 
 
 def _workspace(lib, meta, dev):
@@ -139,8 +149,11 @@ class _Rollout(torch.autograd.Function):
             x0z=_ptr(x0z), cost=_ptr(cost))
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
+            ev = _events(meta, "forward")
             _lib.check(lib.mfb_rollout_forward(C.byref(meta.desc), C.byref(io), meta.dtype_code, C.c_void_p(stream)),
                        "mfb_rollout_forward")
+            if ev is not None:
+                ev[2].record()
         ctx.meta = meta
         ctx.set_materialize_grads(False)     # unused outputs (e.g. the 2 x (B,T,N,3) forces) give None, not zeros
         ctx.save_for_backward(z, mu, controls, x0, xd0, R0, om0, Xs, Xds, Rs, Oms, x0z)
@@ -184,8 +197,11 @@ class _Rollout(torch.autograd.Function):
             g_R0=_ptr(g_R0), g_omega0=_ptr(g_om0))
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
+            ev = _events(meta, "backward")
             _lib.check(lib.mfb_rollout_backward(C.byref(meta.desc), C.byref(io), C.byref(grads), meta.dtype_code,
                                                 C.c_void_p(stream)), "mfb_rollout_backward")
+            if ev is not None:
+                ev[2].record()
         return g_z, g_mu, g_c, g_x0, g_xd0, g_R0, g_om0, None
 
 
@@ -200,6 +216,7 @@ class DPhysics(torch.nn.Module):
         tensors (they are returned as empty tensors) - the training path only needs states.
       * ``fused_cost`` (False): when True the kernel also emits the per-trajectory traversal
         cost ``norm(F_springs).std(-1).std(-1)`` (monoforce_node.py:91) in ``last_cost``.
+      * ``timings`` (None): set to a list to collect CUDA events around each library call.
     """
 
     def __init__(self, dphys_cfg=None, device='cpu'):
@@ -223,6 +240,7 @@ class DPhysics(torch.nn.Module):
         self.return_forces = True
         self.fused_cost = False
         self.last_cost = None
+        self.timings = None      # set to a list to collect (name, start_event, end_event) around every library call
         self._const_cache = {}
 
     # The two integrators exist as named methods because callers select them through
@@ -283,6 +301,7 @@ class DPhysics(torch.nn.Module):
         meta.want_cost = bool(self.fused_cost) and variant == _lib.MFB_STEP_LOOP
         meta.dtype_code = _lib.MFB_F32 if dtype == torch.float32 else _lib.MFB_F64
         meta.B, meta.T, meta.N = B, T, pts.shape[0]
+        meta.timings = self.timings
         cast = lambda t: t.to(device=dev, dtype=dtype)
         Xs, Xds, Rs, Oms, Fs, Ff, x0z, cost = _Rollout.apply(cast(z), cast(mu), controls, cast(x0), cast(xd0),
                                                               cast(R0), cast(om0), meta)

@@ -1,0 +1,148 @@
+"""CPU tests: host-side logic, the C ABI surface (no compute calls without a GPU), multi-process plumbing."""
+import ctypes as C
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers_mfb import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from monoforce_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "monoforce_b200.h")).read()
+    declared = set(re.findall(r"\b(mfb_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    lib = _lib.load()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.mfb_abi_version() == 1
+    assert _lib.kernel_launches() >= 0
+
+
+def test_struct_layouts_match_header_sizes():
+    from monoforce_b200 import _lib
+    # 8 int32 + int64 + 9 doubles + 9 doubles
+    assert C.sizeof(_lib.RolloutDesc) == 8 * 4 + 8 + 9 * 8 + 9 * 8
+    assert C.sizeof(_lib.RolloutBuffers) == 18 * 8 + 8 + 8
+    assert C.sizeof(_lib.RolloutGrads) == 14 * 8
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
+    from monoforce_b200 import _lib
+    lib = _lib.load()
+    d = _lib.RolloutDesc(B=4, T=10, N=223, H=64, W=64, n_tracks=4, variant=0, map_stride=0, mass=60., gravity=9.81,
+                         stiffness=5e4, damping=3464., grid_res=0.1, d_max=6.4, dt=0.01, omega_max=2., robot_Ly=.5)
+    assert lib.mfb_rollout_workspace_bytes(C.byref(d), _lib.MFB_F32) == 64 * 64 * 14 * 4
+    io = _lib.RolloutBuffers()
+    assert lib.mfb_rollout_forward(C.byref(d), C.byref(io), _lib.MFB_F32, None) == -1
+    assert b"NULL" in lib.mfb_last_error()
+    for field, val, msg in (("N", 300, b"N must be"), ("W", 32, b"H must equal W"), ("n_tracks", 3, b"n_tracks"),
+                            ("variant", 7, b"variant"), ("B", 0, b"B and T")):
+        bad = _lib.RolloutDesc.from_buffer_copy(d)
+        setattr(bad, field, val)
+        assert lib.mfb_rollout_forward(C.byref(bad), C.byref(io), _lib.MFB_F32, None) == -1
+        assert msg in lib.mfb_last_error(), (field, lib.mfb_last_error())
+        assert lib.mfb_rollout_workspace_bytes(C.byref(bad), _lib.MFB_F32) == -1
+
+
+def test_config_mirrors_reference_attribute_bag():
+    from monoforce_b200 import DPhysConfig
+    cfg = DPhysConfig(robot="marv", grid_res=0.05)
+    assert cfg.robot_points.shape == (223, 3) and cfg.robot_points.dtype == torch.float32     # diff_physics.ipynb:217
+    assert [int(m.sum()) for m in cfg.driving_parts] == [34, 34, 35, 34]
+    assert cfg.x_grid.shape == (256, 256) and cfg.z_grid.shape == (256, 256)
+    assert cfg.robot_mass == 60. and cfg.use_odeint is True and cfg.dt == 0.01
+    assert abs(float(cfg.damping) - np.sqrt(4 * 60 * 50_000.)) < 1e-9
+    t = DPhysConfig(robot="tradr")
+    assert t.robot_points.shape == (175, 3) and len(t.driving_parts) == 2 and t.robot_mass == 40.
+    assert int((t.part_id >= 0).sum()) == 90
+    with pytest.raises(ValueError):
+        DPhysConfig(robot="spot")
+    with pytest.raises(AssertionError):
+        DPhysConfig(robot="husky")        # no husky mesh is shipped by the reference either (dphys_config.py:25)
+
+
+def test_module_surface_and_no_cpu_fallback():
+    from monoforce_b200 import DPhysics, DPhysConfig, generate_controls, vw_to_track_vels
+    cfg = DPhysConfig(robot="tradr", grid_res=0.4)
+    cfg.traj_sim_time = 0.2
+    sim = DPhysics(cfg, device="cpu")
+    assert sim.x_points.shape == (1, 175, 3) and sim.I_inv.shape == (1, 3, 3) and sim.ts.shape == (20,)
+    controls, stamps = generate_controls(n_trajs=3, time_horizon=0.2, dt=0.01)
+    assert controls.shape == (3, 20, 2) and stamps.shape == (20,)
+    assert torch.equal(controls[:, 0], controls[:, -1])
+    tv = vw_to_track_vels(torch.tensor([1.0]), torch.tensor([0.5]), cfg.robot_size, 2)
+    assert tv.shape == (1, 2) and tv[0, 0] < tv[0, 1]
+    with pytest.raises(ValueError):
+        vw_to_track_vels(torch.tensor([1.0]), torch.tensor([0.5]), cfg.robot_size, 3)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        sim(cfg.z_grid.repeat(3, 1, 1), controls)
+    state = (torch.zeros(3, 3), torch.zeros(3, 3), torch.eye(3).repeat(3, 1, 1), torch.zeros(3, 3))
+    with pytest.raises(AssertionError, match="Controls shape"):       # same message as dphysics.py:575
+        sim(cfg.z_grid.repeat(3, 1, 1), controls[:2], state=state)
+
+
+def test_physics_loss_matches_reference_definition():
+    from monoforce_b200.losses import physics_loss
+    from oracle.dphysics_oracle import physics_loss as ref_loss
+    g = torch.Generator().manual_seed(0)
+    Xp, Xg = torch.randn(5, 40, 3, generator=g), torch.randn(5, 40, 3, generator=g)
+    ts = torch.arange(0, 0.4, 0.01)[None][:, :40]
+    assert torch.allclose(physics_loss((Xp,), (Xg,), ts, ts, 0.9), ref_loss((Xp,), (Xg,), ts, ts, 0.9), rtol=1e-6)
+    gt_ts = torch.tensor([[0.0, 0.1, 0.25, 0.39]])
+    assert torch.allclose(physics_loss((Xp,), (Xg[:, :4],), ts, gt_ts, 0.5), ref_loss((Xp,), (Xg[:, :4],), ts, gt_ts, 0.5))
+
+
+def test_shard_bounds_cover_batch_exactly():
+    from monoforce_b200.dist import shard_bounds
+    for n, w in ((4096, 8), (65536, 8), (10, 3), (7, 8), (1, 1)):
+        spans = [shard_bounds(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from monoforce_b200.dist import shard, gather_costs, best_trajectory, allreduce_map_grads
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    all_costs = torch.arange(n, dtype=torch.float32).flip(0) + 0.5          # the same "global" problem on every rank
+    mine = shard(all_costs, rank, world)
+    gathered = gather_costs(mine, n)
+    idx, val = best_trajectory(mine, n)
+    g = torch.full((4, 4), float(rank + 1))
+    allreduce_map_grads(g, None)
+    q.put((rank, torch.equal(gathered, all_costs), idx, val, float(g[0, 0])))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [64, 37])
+def test_two_process_cost_gather_and_grad_allreduce_gloo(n):
+    """world_size-2 gloo run of the N>1 host logic: shard -> gather costs -> argmin; all-reduce of map grads."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, idx, val, gsum in res:
+        assert ok and idx == n - 1 and val == 0.5 and gsum == 3.0
