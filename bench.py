@@ -357,7 +357,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "cpu_baseline": cpu,
-            "loss": float(loss),
+            "loss": float(loss.detach()),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

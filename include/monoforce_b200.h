@@ -127,6 +127,19 @@ int mfb_rollout_backward(const mfb_rollout_desc* desc, const mfb_rollout_buffers
 int mfb_rollout_forward_host(const mfb_rollout_desc* desc, const mfb_rollout_buffers* io,
                              int dtype, int device);
 
+/* ---- terrain encoder: fused lift + splat -------------------------------------------------
+ * Replaces CamEncode.get_depth_feat's soft-max (x) feature outer product (terrain_encoder/lss.py:63-71)
+ * together with LiftSplatShoot.voxel_pooling incl. the sort + QuickCumsum segment sum
+ * (lss.py:238-280, terrain_encoder/utils.py:144-181).  fp32, device pointers, asynchronous on `stream`.
+ *   logits  (B*N, fH, fW, D + C) channels-last rows: D depth logits then C = 64 camera features
+ *   vox     (B*N, D, fH, fW) int32: flat BEV cell ix*Y + iy of each frustum point, -1 if outside the grid
+ *   bev     (B, X, Y, C) channels-last, ZERO-INITIALISED by the caller, accumulated with vector atomics
+ * The backward writes d loss / d logits (same layout as logits) from d loss / d bev. */
+int mfb_lift_splat_forward(const void* logits, const void* vox, void* bev, int B, int N, int D, int C,
+                           int fH, int fW, int X, int Y, void* stream);
+int mfb_lift_splat_backward(const void* logits, const void* vox, const void* g_bev, void* g_logits,
+                            int B, int N, int D, int C, int fH, int fW, int X, int Y, void* stream);
+
 /* ---- bookkeeping ------------------------------------------------------------------------- */
 const char* mfb_last_error(void);
 int mfb_abi_version(void);

@@ -25,6 +25,7 @@ static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+int fail_status(int code, const std::string& msg) { return fail(code, msg); }   // for the other translation units
 
 static const char* check_desc(const mfb_rollout_desc* d) {
     if (!d) return "desc is NULL";
