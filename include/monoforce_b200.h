@@ -140,6 +140,15 @@ int mfb_lift_splat_forward(const void* logits, const void* vox, void* bev, int B
 int mfb_lift_splat_backward(const void* logits, const void* vox, const void* g_bev, void* g_logits,
                             int B, int N, int D, int C, int fH, int fW, int X, int Y, void* stream);
 
+/* ---- terrain encoder: dense convolution on tcgen05 tensor cores ----------------------------
+ * Replaces the Conv2d -> BatchNorm2d(eval) -> activation triples of the encoder's dense layers
+ * (Up.conv terrain_encoder/lss.py:34-41, BevEncode heads lss.py:117-139, depthnet lss.py:58):
+ *   y[n,h,w,co] = act(scale[co] * conv_KSxKS_same(x, wgt)[n,h,w,co] + shift[co])
+ * x (N,H,W,Cin) and y (N,H,W,Cout) are NHWC bf16, wgt (Cout, KS, KS, Cin) bf16, scale/shift (Cout,) fp32.
+ * KS in {1,3}, stride 1, zero padding KS/2, Cin % 64 == 0, Cout % 64 == 0; act: 0 none, 1 ReLU, 2 GELU(erf). */
+int mfb_conv_bn_act_bf16(const void* x, const void* wgt, const void* scale, const void* shift, void* y,
+                         int N, int H, int W, int Cin, int Cout, int KS, int act, void* stream);
+
 /* ---- bookkeeping ------------------------------------------------------------------------- */
 const char* mfb_last_error(void);
 int mfb_abi_version(void);

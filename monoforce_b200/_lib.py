@@ -16,7 +16,7 @@ MFB_STEP_LOOP, MFB_ODEINT_EULER = 0, 1
 
 EXPORTED_SYMBOLS = (
     "mfb_rollout_workspace_bytes", "mfb_rollout_forward", "mfb_rollout_backward", "mfb_rollout_forward_host",
-    "mfb_lift_splat_forward", "mfb_lift_splat_backward",
+    "mfb_lift_splat_forward", "mfb_lift_splat_backward", "mfb_conv_bn_act_bf16",
     "mfb_last_error", "mfb_abi_version", "mfb_kernel_launches", "mfb_release_scratch",
 )
 
@@ -75,6 +75,8 @@ def load() -> C.CDLL:
     lib.mfb_lift_splat_forward.restype = C.c_int
     lib.mfb_lift_splat_backward.argtypes = [C.c_void_p] * 4 + [C.c_int] * 8 + [C.c_void_p]
     lib.mfb_lift_splat_backward.restype = C.c_int
+    lib.mfb_conv_bn_act_bf16.argtypes = [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_void_p]
+    lib.mfb_conv_bn_act_bf16.restype = C.c_int
     lib.mfb_last_error.restype = C.c_char_p
     lib.mfb_abi_version.restype = C.c_int
     lib.mfb_kernel_launches.restype = C.c_longlong

@@ -1,0 +1,244 @@
+// K4: dense KxK (K = 1 or 3), stride-1, "same"-padded convolution as an implicit GEMM on the 5th-gen tensor
+// cores (tcgen05.mma, accumulator in TMEM, operands staged by TMA), with the folded BatchNorm + activation
+// epilogue of the terrain encoder's dense layers:
+//     Up.conv (two 3x3 conv-BN-GELU)        terrain_encoder/lss.py:34-41
+//     BevEncode heads (3x3 conv-BN-GELU)    terrain_encoder/lss.py:117-139
+//     1x1 depthnet                          terrain_encoder/lss.py:58
+//
+//   y[n,h,w,co] = act( scale[co] * sum_{dy,dx,ci} x[n,h+dy-p,w+dx-p,ci] * wgt[co,dy,dx,ci] + shift[co] )
+//
+// Layouts: x, y NHWC bf16; wgt [Cout][KS*KS*Cin] bf16 (K-major); scale / shift fp32.
+// Tiling: one CTA = 128 output pixels (TH x TW = 8 x 16 patch of one image) x BLOCK_N output channels.
+// The K loop runs over (tap, 64-channel chunk): for each, TMA loads the SHIFTED activation patch as a 4-D box
+// {64 ch, TW, TH, 1} (out-of-image rows/columns are zero-filled by the TMA unit == the conv's zero padding) and
+// the matching weight slab {64, BLOCK_N}; both land in 128-byte-swizzled K-major shared tiles, the canonical
+// UMMA operand layout, so no im2col buffer ever exists.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2-5 = epilogue (tcgen05.ld -> scale/shift/activation -> bf16 -> 16-byte global stores).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mfb {
+namespace conv {
+
+constexpr int kBlockM = 128;      // output pixels per CTA
+constexpr int kTileW = 16;        // patch width  (pixels)
+constexpr int kTileH = 8;         // patch height (pixels)
+constexpr int kBlockK = 64;       // bf16 channels per K chunk = one 128-byte swizzle row
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+
+enum Act : int { kNone = 0, kRelu = 1, kGelu = 2 };
+
+struct Params {
+    int N, H, W, Cin, Cout, KS, act;
+    int tiles_w, tiles_h;
+    __nv_bfloat16* y;
+    const float* scale;
+    const float* shift;
+};
+
+template <int BLOCK_N>
+struct Smem {
+    static constexpr int kABytes = kBlockM * kBlockK * 2;        // 16 KB
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarrierOffset = kStages * kStageBytes;
+    static constexpr int kTotal = kBarrierOffset + 256 + 1024;    // barriers + slack for 1024-byte alignment
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(s_addr(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 :: "r"(s_addr(dst)), "l"(map), "r"(s_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(s_addr(dst)), "l"(map), "r"(s_addr(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(s_addr(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" :: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(s_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, SM100 version 1):
+// start address >> 4 | LBO = 1 (unused for swizzled K-major) | SBO = 1024 B (8 rows x 128 B) | SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(const void* smem_tile) {
+    const uint64_t addr = (uint64_t)(s_addr(smem_tile) >> 4) & 0x3FFFull;
+    return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == kRelu) return fmaxf(v, 0.f);
+    if (act == kGelu) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));     // nn.GELU() (erf form)
+    return v;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);    // SWIZZLE_128B needs 1024-B alignment
+    using S = Smem<BLOCK_N>;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarrierOffset);
+    uint64_t* empty = full + kStages;
+    uint64_t* acc_ready = empty + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile coordinates
+    const int tile = blockIdx.x;
+    const int tw = tile % p.tiles_w;
+    const int th = (tile / p.tiles_w) % p.tiles_h;
+    const int n = tile / (p.tiles_w * p.tiles_h);
+    const int w0 = tw * kTileW, h0 = th * kTileH;
+    const int n0 = blockIdx.y * BLOCK_N;
+    const int pad = p.KS / 2;
+    const int chunks_per_tap = p.Cin / kBlockK;
+    const int k_iters = p.KS * p.KS * chunks_per_tap;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_w) : "memory");
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(acc_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N);          // BLOCK_N fp32 accumulator columns (power of two >= 32)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            for (int i = 0; i < k_iters; ++i) {
+                const int s = i % kStages;
+                const uint32_t round = i / kStages;
+                mbar_wait(empty + s, (round & 1) ^ 1);
+                const int tap = i / chunks_per_tap, c0 = (i - tap * chunks_per_tap) * kBlockK;
+                const int dy = tap / p.KS, dx = tap - dy * p.KS;
+                uint8_t* a_dst = smem + s * S::kStageBytes;
+                uint8_t* b_dst = a_dst + S::kABytes;
+                mbar_expect_tx(full + s, S::kStageBytes);
+                tma_load_4d(a_dst, &tmap_x, full + s, c0, w0 + dx - pad, h0 + dy - pad, n);
+                tma_load_2d(b_dst, &tmap_w, full + s, tap * p.Cin + c0, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer (one thread) =====
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+            for (int i = 0; i < k_iters; ++i) {
+                const int s = i % kStages;
+                const uint32_t round = i / kStages;
+                mbar_wait(full + s, round & 1);
+                tc_fence_after();
+                const uint8_t* a_src = smem + s * S::kStageBytes;
+                const uint64_t a_desc = make_kmajor_sw128_desc(a_src);
+                const uint64_t b_desc = make_kmajor_sw128_desc(a_src + S::kABytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
+                    umma_bf16(tmem_acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0);
+                }
+                umma_commit(empty + s);                      // frees the stage once these MMAs have read it
+            }
+            umma_commit(acc_ready);                          // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+        const int q = warp & 3;
+        mbar_wait(acc_ready, 0);
+        tc_fence_after();
+        const int m = q * 32 + lane;                         // accumulator row == pixel inside the patch
+        const int hh = m / kTileW, ww = m - hh * kTileW;
+        const int h = h0 + hh, w = w0 + ww;
+        const bool in_image = (h < p.H) && (w < p.W);
+        __nv_bfloat16* out = p.y + (((long long)n * p.H + h) * p.W + w) * p.Cout + n0;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
+            if (in_image) {
+                uint32_t packed[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const int co = n0 + c + j;
+                    const float v0 = apply_act(__uint_as_float(r[j]) * __ldg(p.scale + co) + __ldg(p.shift + co), p.act);
+                    const float v1 = apply_act(__uint_as_float(r[j + 1]) * __ldg(p.scale + co + 1) + __ldg(p.shift + co + 1), p.act);
+                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+                    packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(out + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_acc, BLOCK_N);
+}
+
+}  // namespace conv
+}  // namespace mfb

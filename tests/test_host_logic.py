@@ -15,7 +15,7 @@ from helpers_mfb import ROOT
 def test_library_exports_every_declared_symbol():
     from monoforce_b200 import _lib
     header = open(os.path.join(ROOT, "include", "monoforce_b200.h")).read()
-    declared = set(re.findall(r"\b(mfb_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(mfb_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     lib = _lib.load()
     for sym in declared:
