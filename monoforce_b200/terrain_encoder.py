@@ -11,7 +11,10 @@ What runs where:
     (csrc/lift_splat.cu): per frustum pixel, depth soft-max in registers, then depth-weighted features
     are scatter-added straight into the channels-last BEV grid.  The (B,N,C,D,fH,fW) lifted tensor
     (395 MB at B=16) and the argsort are never materialised.  Backward is a gather kernel.
-  * dense convolutions go through torch (cuDNN) in fp32, which is the parity path.
+  * dense convolutions go through torch (cuDNN) in fp32 by default, which is the parity path.  With
+    `net.fast_inference = True` (eval mode only) the GEMM-shaped layers - `Up` blocks, the 1x1 `depthnet`,
+    the three BEV heads - run as bf16 implicit GEMMs on the tcgen05 tensor cores with eval-mode BatchNorm and
+    the activation fused into the epilogue (csrc/conv_tcgen05.cuh); depthwise / strided convs stay on cuDNN.
 The frustum geometry (`get_geometry`, lss.py:204-224) is a handful of tiny 3x3 ops kept in torch.
 """
 from __future__ import annotations
@@ -22,8 +25,7 @@ import torch
 from torch import nn
 from torchvision.models.resnet import resnet18
 
-from . import _lib
-from .dphys_config import DPhysConfig
+from . import _lib, ops
 from .efficientnet import EfficientNet
 
 _H_MAX = 2.0      # DPhysConfig().h_max, the default range of ScaledTanh (lss.py:15-19)
@@ -64,6 +66,34 @@ class Up(nn.Module):
     def forward(self, x1, x2):
         return self.conv(torch.cat([x2, self.up(x1)], dim=1))
 
+    def fast_nhwc(self, x1, x2):
+        """Inference path: NCHW fp32 in, NHWC bf16 out, both conv-BN-GELU triples on the tensor cores."""
+        x = torch.cat([x2, self.up(x1)], dim=1)
+        f = _folded(self, lambda: [ops.fold_conv_bn(self.conv[0], self.conv[1]), ops.fold_conv_bn(self.conv[3], self.conv[4])])
+        x = _to_nhwc_bf16(x, f[0][0].shape[-1])
+        x = ops.conv_bn_act_nhwc(x, *f[0], ops.ACT_GELU)
+        return ops.conv_bn_act_nhwc(x, *f[1], ops.ACT_GELU)
+
+
+def _to_nhwc_bf16(x, c_padded):
+    """(N,C,H,W) float -> (N,H,W,c_padded) bf16 with zero channel padding."""
+    N, Cc, H, W = x.shape
+    if Cc == c_padded:
+        return x.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
+    out = torch.zeros(N, H, W, c_padded, dtype=torch.bfloat16, device=x.device)
+    out[..., :Cc] = x.permute(0, 2, 3, 1)
+    return out
+
+
+def _folded(module, build):
+    """Per-module cache of folded (weights, scale, shift); dropped whenever train() / eval() is toggled."""
+    cache = module.__dict__.get("_mfb_folded")
+    if cache is None:
+        with torch.no_grad():
+            cache = build()
+        module.__dict__["_mfb_folded"] = cache
+    return cache
+
 
 class CamEncode(nn.Module):
     """EfficientNet-B0 trunk -> Up(320+112 -> 512) -> 1x1 `depthnet` giving D depth logits + C features
@@ -101,6 +131,22 @@ class CamEncode(nn.Module):
     def depth_logits_and_feats(self, x):
         return self.depthnet(self.get_eff_depth(x))
 
+    def fast_logits_nhwc(self, x):
+        """Inference path: (BN, fH, fW, D + C) fp32 rows for the lift-splat kernel; `up1` and `depthnet` on tcgen05."""
+        t = self.trunk
+        x = t._swish(t._bn0(t._conv_stem(x)))
+        feats, prev = [], x
+        for block in t._blocks:
+            x = block(x)
+            if prev.size(2) > x.size(2):
+                feats.append(prev)
+            prev = x
+        feats.append(x)
+        y = self.up1.fast_nhwc(feats[4], feats[3])                           # (BN, fH, fW, 512) bf16
+        f = _folded(self, lambda: _fold_padded_cout(self.depthnet))
+        logits = ops.conv_bn_act_nhwc(y, *f, ops.ACT_NONE)                    # (BN, fH, fW, 128) bf16, 123 used
+        return logits[..., :self.D + self.C].float().contiguous()
+
     def get_depth_feat(self, x):
         x = self.depth_logits_and_feats(x)
         depth = self.get_depth_dist(x[:, :self.D])
@@ -108,6 +154,17 @@ class CamEncode(nn.Module):
 
     def forward(self, x):
         return self.get_depth_feat(x)[1]
+
+
+def _fold_padded_cout(conv, multiple=64):
+    """1x1 conv whose Cout is not a multiple of 64 (depthnet: D + C = 123): zero-pad the output channels."""
+    w, scale, shift = ops.fold_conv_bn(conv, None)
+    Cout = w.shape[0]
+    cp = (Cout + multiple - 1) // multiple * multiple
+    wp = torch.zeros(cp, *w.shape[1:], dtype=w.dtype, device=w.device)
+    wp[:Cout] = w
+    pad = lambda v, fill: torch.cat([v, torch.full((cp - Cout,), fill, device=v.device)])
+    return wp.contiguous(), pad(scale, 1.0), pad(shift, 0.0)
 
 
 def _head(outC, act):
@@ -137,6 +194,22 @@ class BevEncode(nn.Module):
     def forward(self, x):
         x = self.backbone(x)
         geom, diff, friction = self.up_geom(x), self.up_diff(x), self.up_friction(x)
+        return {'geom': geom, 'terrain': geom - diff, 'diff': diff, 'friction': friction}
+
+    def fast_forward(self, x):
+        """Inference path: `up1` and the three head convs (one fused 256 -> 3x128 launch) on tcgen05."""
+        x1 = self.layer1(self.relu(self.bn1(self.conv1(x))))
+        y = self.up1.fast_nhwc(self.layer3(self.layer2(x1)), x1)              # (B, X/2, Y/2, 256) bf16
+        heads = (self.up_geom, self.up_diff, self.up_friction)
+
+        def build():
+            parts = [ops.fold_conv_bn(h[1], h[2]) for h in heads]
+            return [torch.cat([p[i] for p in parts]).contiguous() for i in range(3)]
+        f = _folded(self, build)
+        up = heads[0][0](y.permute(0, 3, 1, 2).float())                       # shared x2 bilinear up-sampling
+        z = ops.conv_bn_act_nhwc(_to_nhwc_bf16(up, 256), *f, ops.ACT_GELU)    # (B, X, Y, 384)
+        z = z.permute(0, 3, 1, 2).float()
+        geom, diff, friction = (h[5](h[4](z[:, 128 * i:128 * (i + 1)])) for i, h in enumerate(heads))
         return {'geom': geom, 'terrain': geom - diff, 'diff': diff, 'friction': friction}
 
 
@@ -195,6 +268,12 @@ class LiftSplatShoot(nn.Module):
         self.camencode = CamEncode(self.D, self.camC)
         self.bevencode = BevEncode(inC=self.camC, outC=outC)
         self.use_quickcumsum = True      # kept for attribute compatibility; the fused kernel needs neither path
+        self.fast_inference = False      # opt-in: bf16 tcgen05 path for the dense layers (eval mode only)
+
+    def train(self, mode=True):
+        for m in self.modules():         # folded inference weights are stale once parameters may change
+            m.__dict__.pop("_mfb_folded", None)
+        return super().train(mode)
 
     def create_frustum(self):
         """(D, fH, fW, 3) image-plane sample points (u, v, depth) - lss.py:188-202."""
@@ -239,16 +318,23 @@ class LiftSplatShoot(nn.Module):
         B, N, Cin, H, W = x.shape
         if int(self.nx[2]) != 1:
             raise NotImplementedError("the fused lift-splat kernel assumes a single z voxel (zbound of lss_cfg.yaml)")
-        vox = self.voxel_index(self.get_geometry(rots, trans, intrins, post_rots, post_trans))
-        logits = self.camencode.depth_logits_and_feats(x.view(B * N, Cin, H, W)).float()
-        if not logits.is_cuda:
+        if not x.is_cuda:
             raise RuntimeError("monoforce_b200.LiftSplatShoot runs on CUDA only (fused lift-splat kernel, no CPU fallback)")
+        vox = self.voxel_index(self.get_geometry(rots, trans, intrins, post_rots, post_trans))
+        if self._fast():
+            logits = self.camencode.fast_logits_nhwc(x.view(B * N, Cin, H, W))
+        else:
+            logits = self.camencode.depth_logits_and_feats(x.view(B * N, Cin, H, W)).float().permute(0, 2, 3, 1)
         X, Y = int(self.nx[0]), int(self.nx[1])
-        bev = _LiftSplat.apply(logits.permute(0, 2, 3, 1), vox.view(-1), B, N, self.D, self.camC, X, Y)
+        bev = _LiftSplat.apply(logits, vox.view(-1), B, N, self.D, self.camC, X, Y)
         return bev.permute(0, 3, 1, 2)        # (B, C, X, Y) view of channels-last storage
 
+    def _fast(self):
+        return self.fast_inference and not self.training and not torch.is_grad_enabled()
+
     def forward(self, x, rots, trans, intrins, post_rots, post_trans):
-        return self.bevencode(self.get_voxels(x, rots, trans, intrins, post_rots, post_trans))
+        bev = self.get_voxels(x, rots, trans, intrins, post_rots, post_trans)
+        return self.bevencode.fast_forward(bev) if self._fast() else self.bevencode(bev)
 
     def from_pretrained(self, modelf):
         """Partial-state-dict loading like lss.py:293-302."""

@@ -105,3 +105,23 @@ def test_encoder_feeds_rollout_end_to_end():
     states[0].pow(2).mean().backward()
     gsum = sum(float(p.grad.abs().sum()) for p in net.bevencode.up_geom.parameters() if p.grad is not None)
     assert gsum > 0 and np.isfinite(gsum)
+
+
+def test_fast_inference_path_close_to_fp32_path():
+    """bf16 tcgen05 path for the dense layers vs the fp32 cuDNN path of the same network (eval mode)."""
+    net, grid_conf, aug_conf = _net()
+    net = net.to(DEV)
+    inputs = [t.to(DEV) for t in make_inputs(grid_conf, aug_conf, 2, 6)]
+    with torch.no_grad():
+        ref = net(*inputs)
+        net.fast_inference = True
+        fast = net(*inputs)
+        net.fast_inference = False
+    for k in ("geom", "terrain", "diff", "friction"):
+        assert fast[k].shape == ref[k].shape
+        assert rel_err(fast[k], ref[k]) < 5e-2, k
+        assert (fast[k] - ref[k]).abs().mean().item() < 1e-2 * ref[k].abs().mean().item() + 1e-3, k
+    # with grad enabled (training / fine-tuning) the fp32 autograd path is used regardless of the flag
+    net.fast_inference = True
+    out = net(*inputs)
+    assert out["geom"].requires_grad
