@@ -54,6 +54,7 @@ typedef struct mfb_rollout_desc {
     double mass, gravity, stiffness, damping, grid_res, d_max, dt, omega_max;
     double robot_Ly;      /* robot_size[1] (track gauge), dphys_config.py:43          */
     double I_inv[9];      /* inverse of the body-frame inertia tensor, row-major (dphysics.py:152-153) */
+    double joint_positions[12]; /* (4,3) pivots of the driving parts (dphys_config.py:99-104); used with joint_angles */
 } mfb_rollout_desc;
 
 /* Inputs and outputs of the forward rollout.  Shapes follow DPhysics.forward. */
@@ -69,6 +70,8 @@ typedef struct mfb_rollout_buffers {
     const void* points;     /* (N, 3)   body-frame contact points                     */
     const int32_t* part_id; /* (N,)     driving part of each point or -1              */
     const void* ts;         /* (T,)     solver time grid; required for MFB_ODEINT_EULER, else may be NULL */
+    const void* joint_angles; /* (B, T, 4) flipper angles of the 4 driving parts, or NULL for static geometry
+                               (DPhysics.update_joints, dphysics.py:326-358; forward only) */
     /* outputs */
     void* Xs;               /* (B, T, 3)                                              */
     void* Xds;              /* (B, T, 3)                                              */

@@ -30,10 +30,11 @@ class RolloutDesc(C.Structure):
         ("grid_res", C.c_double), ("d_max", C.c_double), ("dt", C.c_double), ("omega_max", C.c_double),
         ("robot_Ly", C.c_double),
         ("I_inv", C.c_double * 9),
+        ("joint_positions", C.c_double * 12),
     ]
 
 
-_IN = ("z_grid", "friction", "controls", "x0", "xd0", "R0", "omega0", "points", "part_id", "ts")
+_IN = ("z_grid", "friction", "controls", "x0", "xd0", "R0", "omega0", "points", "part_id", "ts", "joint_angles")
 _OUT = ("Xs", "Xds", "Rs", "Omegas", "F_springs", "F_frictions", "x0z", "cost")
 
 

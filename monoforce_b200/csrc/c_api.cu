@@ -62,6 +62,8 @@ static RolloutArgs<T> make_args(const mfb_rollout_desc& d, const mfb_rollout_buf
     a.z = (const T*)io.z_grid; a.mu = (const T*)io.friction; a.controls = (const T*)io.controls;
     a.x0 = (const T*)io.x0; a.xd0 = (const T*)io.xd0; a.R0 = (const T*)io.R0; a.om0 = (const T*)io.omega0;
     a.pts = (const T*)io.points; a.part = io.part_id; a.ts = (const T*)io.ts;
+    a.joint_angles = (const T*)io.joint_angles;
+    for (int i = 0; i < 12; ++i) a.joint_pos[i] = (T)d.joint_positions[i];
     a.cells = (const T*)io.workspace;
     a.cell_stride = d.map_stride == 0 ? 0 : (long long)d.H * d.W * kCellRec;
     a.Xs = (T*)io.Xs; a.Xds = (T*)io.Xds; a.Rs = (T*)io.Rs; a.Oms = (T*)io.Omegas;
@@ -129,6 +131,8 @@ template <typename T>
 static int backward_typed(const mfb_rollout_desc& d, const mfb_rollout_buffers& io, const mfb_rollout_grads& g,
                           cudaStream_t st) {
     RolloutArgs<T> a = make_args<T>(d, io);
+    if (a.joint_angles)
+        return fail(MFB_ERR_UNSUPPORTED, "the adjoint of the moving-flipper variant (joint_angles != NULL) is not implemented");
     if (int rc = build_table<T>(d, io, st)) return rc;
     AdjointArgs<T> ga;
     ga.g_Xs = (const T*)g.g_Xs; ga.g_Xds = (const T*)g.g_Xds; ga.g_Rs = (const T*)g.g_Rs; ga.g_Oms = (const T*)g.g_Omegas;

@@ -36,6 +36,8 @@ struct RolloutArgs {
     const T* pts;                // (N,3) body-frame contact points
     const int* part;             // (N,) driving part id or -1
     const T* ts;                 // (T,) solver time grid (odeint variant only)
+    const T* joint_angles;       // (B, T, 4) flipper angles or nullptr (static geometry)      dphysics.py:326-358
+    T joint_pos[12];             // pivot of each driving part, row-major (4,3)               dphys_config.py:99-104
     const T* cells;              // (n_maps, H, W, 12) packed cell table built by build_cell_table (workspace)
     long long cell_stride;       // elements between two trajectories' tables, 0 = shared
     // outputs
@@ -342,6 +344,36 @@ __device__ __forceinline__ void eval_point(PointEval<T>& o, const StepFrame<T>& 
     o.sl[0] = o.d[0] - o.dn * n0; o.sl[1] = o.d[1] - o.dn * n1; o.sl[2] = o.d[2] - o.dn * n2;
 }
 
+// ------------------------------------------------------------------------------------------
+// moving flippers (dphysics.py:326-358) and the per-step inverse inertia tensor (:196-197, :107-141)
+// ------------------------------------------------------------------------------------------
+// Lane i < 4 holds (cos, sin) of flipper angle i; a point of driving part q is rotated about the y axis
+// through the part's pivot:  p' = Ry(angle_q) (p - pivot_q) + pivot_q.
+template <typename T>
+__device__ __forceinline__ void articulate_point(T& px, T& py, T& pz, int part, T my_cos, T my_sin, const T* joint_pos) {
+    const int src = part < 0 ? 0 : part;
+    const T c = __shfl_sync(kFull, my_cos, src), s = __shfl_sync(kFull, my_sin, src);
+    if (part >= 0) {
+        const T ox = joint_pos[part * 3 + 0], oz = joint_pos[part * 3 + 2];
+        const T dx = px - ox, dz = pz - oz;
+        px = c * dx + s * dz + ox;
+        pz = -s * dx + c * dz + oz;
+    }
+}
+
+// inverse of the symmetric point-mass inertia tensor from the six warp-reduced second moments
+// m6 = (sum y^2+z^2, sum x^2+z^2, sum x^2+y^2, sum xy, sum xz, sum yz) * (mass / N)
+template <typename T>
+__device__ __forceinline__ void invert_inertia(const T* m6, T* inv9) {
+    const T a = m6[0], d = m6[1], f = m6[2], b = -m6[3], c = -m6[4], e = -m6[5];     // [[a,b,c],[b,d,e],[c,e,f]]
+    const T A = d * f - e * e, B = c * e - b * f, Cc = b * e - c * d;
+    const T det = a * A + b * B + c * Cc;
+    const T r = (T)1 / det;
+    inv9[0] = A * r;            inv9[1] = B * r;            inv9[2] = Cc * r;
+    inv9[3] = B * r;            inv9[4] = (a * f - c * c) * r; inv9[5] = (b * c - a * e) * r;
+    inv9[6] = Cc * r;           inv9[7] = (b * c - a * e) * r; inv9[8] = (a * d - b * b) * r;
+}
+
 // Body points staged once per block: slot = j*32 + lane == point index.  Padded slots (only in
 // the last j) hold the body origin; the kernels zero their soft-contact weight explicitly.
 template <typename T>
@@ -351,6 +383,7 @@ struct PointTable {
     T pz[kMaxPointsPerLane * 32];
     T side[kMaxPointsPerLane * 32];   // 0: not driven, -half_Ly: left track, +half_Ly: right track
     T driven[kMaxPointsPerLane * 32]; // 1 if the point belongs to a driving part else 0
+    int part[kMaxPointsPerLane * 32]; // driving part id or -1 (needed only when flippers move)
 };
 
 template <typename T>
@@ -362,11 +395,12 @@ __device__ __forceinline__ void fill_point_table(PointTable<T>& tab, const Rollo
             tab.pz[p] = a.pts[p * 3 + 2];
             const int q = a.part[p];
             // 2 tracks: (left, right); 4 tracks: (FL, FR, RL, RR) -> odd index = right (dphysics.py:75-104)
+            tab.part[p] = q;
             tab.driven[p] = q >= 0 ? (T)1 : (T)0;
             tab.side[p] = q < 0 ? (T)0 : ((q & 1) ? a.half_Ly : -a.half_Ly);
         } else {
             tab.px[p] = (T)0; tab.py[p] = (T)0; tab.pz[p] = (T)0;
-            tab.driven[p] = (T)0; tab.side[p] = (T)0;
+            tab.driven[p] = (T)0; tab.side[p] = (T)0; tab.part[p] = -1;
         }
     }
 }

@@ -25,6 +25,12 @@ static LaunchError launch_ppl(const RolloutArgs<T>& a, cudaStream_t st) {
         count_launch();
         return {nullptr};
     };
+    if (a.joint_angles) {
+        // moving flippers (marv): one instantiation per integrator, forces + cost handled at run time would bloat the
+        // build, so this variant always materialises forces and never fuses the cost
+        if (!forces || cost) return {"the moving-flipper variant needs F_springs/F_frictions and does not fuse the cost"};
+        return go(rollout_fwd_kernel<T, PPL, VARIANT, true, false, true>);
+    }
     if (VARIANT == kOdeintEuler) {
         if (cost) return {"cost output is defined for the step-loop variant only"};
         if (forces) return go(rollout_fwd_kernel<T, PPL, VARIANT, true, false>);

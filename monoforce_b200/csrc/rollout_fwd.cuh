@@ -61,7 +61,7 @@ __device__ __forceinline__ void emit_rows(T* __restrict__ grow_s, T* __restrict_
     }
 }
 
-template <typename T, int PPL, int VARIANT, bool FORCES, bool COST>
+template <typename T, int PPL, int VARIANT, bool FORCES, bool COST, bool JOINTS = false>
 __global__ void __launch_bounds__(kFwdWarps * 32, (sizeof(T) == 4 && PPL <= 7) ? 4 : 1)
 rollout_fwd_kernel(const RolloutArgs<T> a) {
     __shared__ PointTable<T> tab;
@@ -165,11 +165,26 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
         T nrm[PPL][3], sc[PPL], slip[PPL][3], arm[PPL][3];
         T C = (T)0;
 
+        // moving flippers: lane i < 4 owns (cos, sin) of joint angle i at this step     dphysics.py:187-197
+        T jc = (T)1, js = (T)0, mom[6] = {0, 0, 0, 0, 0, 0};
+        if (JOINTS) {
+            const T ang = lane < 4 ? a.joint_angles[((long long)b * a.nT + t) * 4 + lane] : (T)0;
+            Mth<T>::sincos(ang, &js, &jc);
+        }
+
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
             const int slot = j * 32 + lane;
+            T px = tab.px[slot], py = tab.py[slot], pz = tab.pz[slot];
+            if (JOINTS) {
+                articulate_point(px, py, pz, tab.part[slot], jc, js, a.joint_pos);
+                if ((j < PPL - 1) || last_valid) {
+                    mom[0] += py * py + pz * pz; mom[1] += px * px + pz * pz; mom[2] += px * px + py * py;
+                    mom[3] += px * py; mom[4] += px * pz; mom[5] += py * pz;
+                }
+            }
             PointEval<T> e;
-            eval_point(e, f, tab.px[slot], tab.py[slot], tab.pz[slot], tab.driven[slot], tab.side[slot],
+            eval_point(e, f, px, py, pz, tab.driven[slot], tab.side[slot],
                        (j < PPL - 1) || last_valid, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
             C += e.cw;
             sc[j] = e.sp * e.cw;
@@ -248,9 +263,20 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
 
         // angular / linear acceleration                                         dphysics.py:255-266
         T wd[3], vd[3];
+        T Iinv[9];
+        if (JOINTS) {
+            // inertia of the articulated point set about the body origin, inverted every step      dphysics.py:196-197
+            const T mp = a.mass / (T)a.N;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) mom[k] = warp_sum(mom[k]) * mp;
+            invert_inertia(mom, Iinv);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Iinv[k] = a.Iinv[k];
+        }
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            wd[r] = clampT(a.Iinv[r * 3 + 0] * sum[3] + a.Iinv[r * 3 + 1] * sum[4] + a.Iinv[r * 3 + 2] * sum[5], a.omega_max);
+            wd[r] = clampT(Iinv[r * 3 + 0] * sum[3] + Iinv[r * 3 + 1] * sum[4] + Iinv[r * 3 + 2] * sum[5], a.omega_max);
         }
         vd[0] = sum[0] * a.inv_mass;
         vd[1] = sum[1] * a.inv_mass;

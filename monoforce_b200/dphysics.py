@@ -96,7 +96,8 @@ def _ptr(t):
 
 class _RolloutMeta:
     """Everything that is not a differentiable tensor."""
-    __slots__ = ("desc", "points", "part_id", "ts", "want_forces", "want_cost", "dtype_code", "B", "T", "N", "timings")
+    __slots__ = ("desc", "points", "part_id", "ts", "want_forces", "want_cost", "dtype_code", "B", "T", "N", "timings",
+                 "joint_angles")
 
 
 def _require_cuda(*tensors):
@@ -145,6 +146,7 @@ class _Rollout(torch.autograd.Function):
             workspace=_ptr(ws), workspace_bytes=ws.numel(),
             z_grid=_ptr(z), friction=_ptr(mu), controls=_ptr(controls), x0=_ptr(x0), xd0=_ptr(xd0), R0=_ptr(R0),
             omega0=_ptr(om0), points=_ptr(meta.points), part_id=_ptr(meta.part_id), ts=_ptr(meta.ts),
+            joint_angles=_ptr(meta.joint_angles),
             Xs=_ptr(Xs), Xds=_ptr(Xds), Rs=_ptr(Rs), Omegas=_ptr(Oms), F_springs=_ptr(Fs), F_frictions=_ptr(Ff),
             x0z=_ptr(x0z), cost=_ptr(cost))
         with torch.cuda.device(dev):
@@ -188,6 +190,7 @@ class _Rollout(torch.autograd.Function):
             workspace=_ptr(ws), workspace_bytes=ws.numel(),
             z_grid=_ptr(z), friction=_ptr(mu), controls=_ptr(controls), x0=_ptr(x0), xd0=_ptr(xd0), R0=_ptr(R0),
             omega0=_ptr(om0), points=_ptr(meta.points), part_id=_ptr(meta.part_id), ts=_ptr(meta.ts),
+            joint_angles=_ptr(meta.joint_angles),
             Xs=_ptr(Xs), Xds=_ptr(Xds), Rs=_ptr(Rs), Omegas=_ptr(Oms), F_springs=None, F_frictions=None,
             x0z=_ptr(x0z), cost=None)
         grads = _lib.RolloutGrads(
@@ -288,6 +291,9 @@ class DPhysics(torch.nn.Module):
         desc.robot_Ly = float(cfg.robot_size[1])
         for i in range(9):
             desc.I_inv[i] = float(I_inv[i])
+        for i, piv in enumerate(list(cfg.joint_positions.values())[:4]):
+            for k in range(3):
+                desc.joint_positions[i * 3 + k] = float(piv[k])
         meta = _RolloutMeta()
         meta.desc, meta.points, meta.part_id = desc, pts, part
         meta.ts = None
@@ -297,8 +303,10 @@ class DPhysics(torch.nn.Module):
                 n_full = int(cfg.traj_sim_time / cfg.dt)
                 ts = torch.linspace(0, cfg.traj_sim_time, n_full, dtype=dtype)[:T]
             meta.ts = ts.to(device=dev).contiguous()
-        meta.want_forces = bool(self.return_forces)
-        meta.want_cost = bool(self.fused_cost) and variant == _lib.MFB_STEP_LOOP
+        moving = self._moving_joints
+        meta.joint_angles = self.joint_angles.to(device=dev, dtype=dtype).contiguous() if moving else None
+        meta.want_forces = bool(self.return_forces) or moving
+        meta.want_cost = bool(self.fused_cost) and variant == _lib.MFB_STEP_LOOP and not moving
         meta.dtype_code = _lib.MFB_F32 if dtype == torch.float32 else _lib.MFB_F64
         meta.B, meta.T, meta.N = B, T, pts.shape[0]
         meta.timings = self.timings
@@ -353,12 +361,17 @@ class DPhysics(torch.nn.Module):
         B = state[0].shape[0]
         assert controls.shape == (B, N_ts, 2), f'Controls shape {controls.shape} != {(B, N_ts, 2)}'
         self.controls = controls
+        self._moving_joints = False
         if joint_angles is not None:
             assert joint_angles.shape == (B, N_ts, 4), f'Joint angles shape {joint_angles.shape} != {(B, N_ts, 4)}'
-            if cfg.robot == 'marv' and bool(torch.any(joint_angles != 0)):
+            # the reference articulates the body only for marv with non-zero angles (:340; one host sync per CALL
+            # here instead of one per step there)
+            self._moving_joints = cfg.robot == 'marv' and bool(torch.any(joint_angles != 0))
+            if self._moving_joints and (torch.is_grad_enabled() and any(
+                    t is not None and t.requires_grad for t in (z_grid, friction, controls, joint_angles, *state))):
                 raise NotImplementedError(
-                    "moving flippers (non-zero joint_angles on marv, dphysics.py:326-358) are not yet "
-                    "implemented in the CUDA rollout; SURVEY.md section 8 row F2")
+                    "gradients through the moving-flipper variant (non-zero joint_angles on marv, dphysics.py:326-358) "
+                    "are not implemented; run it under torch.no_grad()")
         self.joint_angles = joint_angles if joint_angles is not None else \
             torch.zeros((B, N_ts, 4), device=self.device, dtype=dtype)
         self.ts = self.ts[:N_ts]                                                # :581

@@ -27,8 +27,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header_sizes():
     from monoforce_b200 import _lib
     # 8 int32 + int64 + 9 doubles + 9 doubles
-    assert C.sizeof(_lib.RolloutDesc) == 8 * 4 + 8 + 9 * 8 + 9 * 8
-    assert C.sizeof(_lib.RolloutBuffers) == 18 * 8 + 8 + 8
+    assert C.sizeof(_lib.RolloutDesc) == 8 * 4 + 8 + 9 * 8 + 9 * 8 + 12 * 8
+    assert C.sizeof(_lib.RolloutBuffers) == 19 * 8 + 8 + 8
     assert C.sizeof(_lib.RolloutGrads) == 14 * 8
 
 

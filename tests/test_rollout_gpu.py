@@ -360,3 +360,43 @@ def test_full_size_properties_cfg2():
     total = Fs[:, t].sum(1) + Ff[:, t].sum(1)
     total[:, 2] -= cfg.robot_mass * cfg.gravity
     assert ((acc - total).abs().max() / (cfg.robot_mass * cfg.gravity)) < 2e-2
+
+
+def test_moving_flippers_match_reference_golden_fp32():
+    """A8: marv with non-zero joint angles (per-step point articulation + inverse inertia, dphysics.py:192-197, :326-358)."""
+    g = load_golden("marv_hill128_joints_T60_B2")
+    sim, cfg = _module("marv", float(g["grid_res"]), int(g["T"]), "step")
+    B = g["controls"].shape[0]
+    with torch.no_grad():
+        (Xs, Xds, Rs, Oms), (Fs, Ff) = sim(_t(g["z"]).unsqueeze(0).expand(B, -1, -1), _t(g["controls"]),
+                                           joint_angles=_t(g["joint_angles"]))
+    assert rel_err(Xs, g["Xs"]) < 1e-3 and rel_err(Rs, g["Rs"]) < 1e-3
+    keep = g["F_keep_steps"]
+    assert rel_err(Fs[:, keep], g["Fs_keep"]) < 5e-2
+
+
+@pytest.mark.parametrize("variant", ["step", "odeint"])
+def test_moving_flippers_fp64_match_oracle(variant):
+    from oracle import dphysics_oracle as O
+    dtype = torch.float64
+    T, B = 80, 4
+    sim, cfg = _module("marv", 0.1, T, variant, dtype)
+    z, controls, fr, st = _random_case(cfg, B, T, 17, dtype)
+    ramp = torch.linspace(-1.2, 1.2, T, dtype=dtype).repeat(B, 1)
+    ja = torch.stack([ramp, 0.5 * ramp, -ramp, -0.3 * ramp], -1)
+    rs, rf = O.rollout(make_spec(cfg), z.repeat(B, 1, 1), controls, joint_angles=ja, state=st,
+                       friction=fr.repeat(B, 1, 1), variant=variant, dtype=dtype)
+    with torch.no_grad():
+        ks, kf = sim(z.to(DEV).unsqueeze(0), controls.to(DEV), joint_angles=ja.to(DEV), state=tuple(s.to(DEV) for s in st),
+                     friction=fr.to(DEV).unsqueeze(0))
+    for a, b in zip(ks, rs):
+        assert rel_err(a, b) < 1e-9
+    for a, b in zip(kf, rf):
+        assert rel_err(a, b) < 1e-8
+    # zero angles take the static-geometry kernel and gradients work; non-zero angles with grad are refused loudly
+    zk = z.to(DEV).requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        sim(zk.unsqueeze(0), controls.to(DEV), joint_angles=ja.to(DEV))
+    out, _ = sim(zk.unsqueeze(0), controls.to(DEV), joint_angles=torch.zeros_like(ja).to(DEV))
+    out[0].sum().backward()
+    assert torch.isfinite(zk.grad).all()
