@@ -28,7 +28,7 @@ constexpr int kBlockM = 128;      // output pixels per CTA
 constexpr int kTileW = 16;        // patch width  (pixels)
 constexpr int kTileH = 8;         // patch height (pixels)
 constexpr int kBlockK = 64;       // bf16 channels per K chunk = one 128-byte swizzle row
-constexpr int kStages = 4;
+constexpr int kStages = 3;       // 3 x 32 KB: two CTAs fit one SM, so one CTA's epilogue overlaps the other's MMAs
 constexpr int kThreads = 192;
 
 enum Act : int { kNone = 0, kRelu = 1, kGelu = 2 };
@@ -133,7 +133,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);    // SWIZZLE_128B needs 1024-B alignment
