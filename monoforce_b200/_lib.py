@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmonoforce_b200.so")
+# MFB_LIB_PATH lets kernel experiments load an alternative build of the SAME ABI (development only)
+LIB_PATH = os.environ.get("MFB_LIB_PATH") or os.path.join(_PKG, "libmonoforce_b200.so")
 
 MFB_F32, MFB_F64 = 0, 1
 MFB_STEP_LOOP, MFB_ODEINT_EULER = 0, 1

@@ -16,6 +16,9 @@
 namespace mfb {
 
 constexpr int kFwdWarps = 4;   // trajectories per CTA
+#ifndef MFB_FWD_MINB
+#define MFB_FWD_MINB 4        // resident CTAs per SM the fp32 kernel is compiled for (128 registers)
+#endif
 
 // Force rows leave the SM through TMA bulk stores: every lane drops its points' forces into a
 // per-warp shared-memory image of the (N,3) row (stride-3 words across lanes: conflict free), the
@@ -62,7 +65,7 @@ __device__ __forceinline__ void emit_rows(T* __restrict__ grow_s, T* __restrict_
 }
 
 template <typename T, int PPL, int VARIANT, bool FORCES, bool COST, bool JOINTS = false>
-__global__ void __launch_bounds__(kFwdWarps * 32, (sizeof(T) == 4 && PPL <= 7) ? 4 : 1)
+__global__ void __launch_bounds__(kFwdWarps * 32, (sizeof(T) == 4 && PPL <= 7) ? MFB_FWD_MINB : 1)
 rollout_fwd_kernel(const RolloutArgs<T> a) {
     __shared__ PointTable<T> tab;
     fill_point_table(tab, a, PPL * 32);

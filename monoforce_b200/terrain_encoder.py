@@ -134,15 +134,19 @@ class CamEncode(nn.Module):
     def fast_logits_nhwc(self, x):
         """Inference path: (BN, fH, fW, D + C) fp32 rows for the lift-splat kernel; `up1` and `depthnet` on tcgen05."""
         t = self.trunk
-        x = t._swish(t._bn0(t._conv_stem(x)))
-        feats, prev = [], x
-        for block in t._blocks:
-            x = block(x)
-            if prev.size(2) > x.size(2):
-                feats.append(prev)
-            prev = x
-        feats.append(x)
-        y = self.up1.fast_nhwc(feats[4], feats[3])                           # (BN, fH, fW, 512) bf16
+        # the trunk's depthwise / squeeze-excite / strided layers are memory-bound, not GEMM-shaped: they stay on
+        # cuDNN, but in bf16 channels-last so every activation pass moves half the bytes
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            x = x.contiguous(memory_format=torch.channels_last)
+            x = t._swish(t._bn0(t._conv_stem(x)))
+            feats, prev = [], x
+            for block in t._blocks:
+                x = block(x)
+                if prev.size(2) > x.size(2):
+                    feats.append(prev)
+                prev = x
+            feats.append(x)
+        y = self.up1.fast_nhwc(feats[4].float(), feats[3].float())           # (BN, fH, fW, 512) bf16
         f = _folded(self, lambda: _fold_padded_cout(self.depthnet))
         logits = ops.conv_bn_act_nhwc(y, *f, ops.ACT_NONE)                    # (BN, fH, fW, 128) bf16, 123 used
         return logits[..., :self.D + self.C].float().contiguous()
@@ -198,8 +202,10 @@ class BevEncode(nn.Module):
 
     def fast_forward(self, x):
         """Inference path: `up1` and the three head convs (one fused 256 -> 3x128 launch) on tcgen05."""
-        x1 = self.layer1(self.relu(self.bn1(self.conv1(x))))
-        y = self.up1.fast_nhwc(self.layer3(self.layer2(x1)), x1)              # (B, X/2, Y/2, 256) bf16
+        with torch.autocast("cuda", dtype=torch.bfloat16):                   # strided ResNet layers: cuDNN bf16 channels-last
+            x1 = self.layer1(self.relu(self.bn1(self.conv1(x.contiguous(memory_format=torch.channels_last)))))
+            x3 = self.layer3(self.layer2(x1))
+        y = self.up1.fast_nhwc(x3.float(), x1.float())                        # (B, X/2, Y/2, 256) bf16
         heads = (self.up_geom, self.up_diff, self.up_friction)
 
         def build():
