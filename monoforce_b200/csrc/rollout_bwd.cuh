@@ -31,10 +31,15 @@ constexpr int kBwdWarps = 4;
 // memory when the point moves to another cell: ~10x fewer global atomics than one per step.
 // The global target interleaves (d/dz, d/dfriction) per cell so a flush is two 16-byte or four
 // 8-byte vector reductions (red.global.add.v4.f32 / .v2.f32, sm_90+).
+template <typename T> struct Quad;                       // 4 scalars moved as one or two 16-byte shared accesses
+template <> struct __align__(16) Quad<float> { float v[4]; };
+template <> struct __align__(16) Quad<double> { double v[4]; };
+
 template <typename T>
 struct MapGradCache {
+    Quad<T> z[kMaxPointsPerLane * 32];               // d/dz of the point's current cell corners (00, 10, 01, 11)
+    Quad<T> m[kMaxPointsPerLane * 32];               // d/dfriction of the same corners
     int cell[kMaxPointsPerLane * 32];
-    T acc[8][kMaxPointsPerLane * 32];
 };
 
 __device__ __forceinline__ void red_pair(float* p, float a, float b) { atomicAdd(reinterpret_cast<float2*>(p), make_float2(a, b)); }
@@ -66,8 +71,8 @@ __global__ void scatter_map_grads_kernel(const T* __restrict__ g2, T* __restrict
 }
 
 template <typename T>
-__device__ __forceinline__ T gate(T grad, T val, T lim) {   // backward of clamp(val, -lim, lim)
-    return (val >= -lim && val <= lim) ? grad : (T)0;
+__device__ __forceinline__ T gate(T grad, T val, T lim) {   // backward of clamp(val, -lim, lim): passes inside [-lim, lim]
+    return (fabs(val) <= lim) ? grad : (T)0;
 }
 
 // adjoint of E(w) = I + sn K + c1 (k k^T - |k|^2 I) (see rodrigues_right); accumulates into wb
@@ -112,7 +117,7 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
     fill_point_table(tab, a, PPL * 32);
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
+    const int lane = lane_id();
     const int b = blockIdx.x * kBwdWarps + (threadIdx.x >> 5);
     if (b >= a.B) return;
     const int n_last = a.N - (PPL - 1) * 32;
@@ -329,7 +334,9 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             const T f = sc[j] * invC;
             const T G0 = f * nrm[j][0], G1 = f * nrm[j][1], G2 = f * nrm[j][2];
             const T Fr0 = clampT(G0, a.mg), Fr1 = clampT(G1, a.mg), Fr2 = clampT(G2, a.mg);
-            const T Nf = Mth<T>::sqrt(Fr0 * Fr0 + Fr1 * Fr1 + Fr2 * Fr2);
+            const T Nf2 = Fr0 * Fr0 + Fr1 * Fr1 + Fr2 * Fr2;
+            const T Nf_inv = Nf2 > (T)0 ? Mth<T>::rsqrt(Nf2) : (T)0;
+            const T Nf = Nf2 * Nf_inv;
             const T Hh0 = Nf * slip[j][0], Hh1 = Nf * slip[j][1], Hh2 = Nf * slip[j][2];
             const T Ft0 = clampT(Hh0, a.mg), Ft1 = clampT(Hh1, a.mg), Ft2 = clampT(Hh2, a.mg);
             const T F0 = Fr0 + Ft0, F1 = Fr1 + Ft1, F2 = Fr2 + Ft2;
@@ -365,8 +372,8 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             const T Nf_b = Hb0 * slip[j][0] + Hb1 * slip[j][1] + Hb2 * slip[j][2];
             slip[j][0] = Nf * Hb0; slip[j][1] = Nf * Hb1; slip[j][2] = Nf * Hb2;
             // Nf = |F_spring|
-            if (Nf > (T)0) {
-                const T k = Nf_b / Nf;
+            {
+                const T k = Nf_b * Nf_inv;          // d|F|/dF = F / |F| (0 at the origin, like torch.norm)
                 Frb0 += k * Fr0; Frb1 += k * Fr1; Frb2 += k * Fr2;
             }
             // F_spring = clamp(f n)
@@ -378,9 +385,9 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
         const T C_b = -warp_sum(Cb_part) * invC;
 
         // ---------------- pass C: phase 1 again, reversed ----------------
-        T acc[23];
+        T acc[24];
 #pragma unroll
-        for (int k = 0; k < 23; ++k) acc[k] = (T)0;
+        for (int k = 0; k < 24; ++k) acc[k] = (T)0;
         // acc: 0-2 x_bar, 3-5 v_bar, 6-8 w_bar, 9-17 R_bar, 18-20 hd_bar, 21-22 controls
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
@@ -439,20 +446,20 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                                  mu_b * w00, mu_b * w10, mu_b * w01, mu_b * w11};
                 if (e.cell >= 0) {
                     const int cur = wc.cell[slot];
+                    Quad<T> qz = wc.z[slot], qm = wc.m[slot];
                     if (cur == e.cell) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) wc.acc[k][slot] += cg[k];
+                        for (int k = 0; k < 4; ++k) { qz.v[k] += cg[k]; qm.v[k] += cg[4 + k]; }
                     } else {
                         if (cur >= 0) {
-                            T old[8];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) old[k] = wc.acc[k][slot];
+                            const T old[8] = {qz.v[0], qz.v[1], qz.v[2], qz.v[3], qm.v[0], qm.v[1], qm.v[2], qm.v[3]};
                             scatter_corners(gmap, on_map_corners(cur, H, W), old);
                         }
                         wc.cell[slot] = e.cell;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) wc.acc[k][slot] = cg[k];
+                        for (int k = 0; k < 4; ++k) { qz.v[k] = cg[k]; qm.v[k] = cg[4 + k]; }
                     }
+                    wc.z[slot] = qz; wc.m[slot] = qm;
                 } else {
                     const T ggx = e.r[0] * a.inv_res + f.ox, ggy = e.r[1] * a.inv_res + f.oy;
                     scatter_corners(gmap, flat_corners((long long)ggx, (long long)ggy, H, W), cg);
@@ -474,8 +481,7 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             acc[12] += rb1 * px; acc[13] += rb1 * py; acc[14] += rb1 * pz;
             acc[15] += rb2 * px; acc[16] += rb2 * py; acc[17] += rb2 * pz;
         }
-#pragma unroll
-        for (int k = 0; k < 23; ++k) acc[k] = warp_sum(acc[k]);
+        warp_sum8(acc, lane); warp_sum8(acc + 8, lane); warp_sum8(acc + 16, lane);
 
         // fold the per-point sums into the state adjoint (pre-update state)
 #pragma unroll
@@ -547,9 +553,8 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                 const int slot = j * 32 + lane;
                 const int cur = wc.cell[slot];
                 if (cur >= 0) {
-                    T old[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) old[k] = wc.acc[k][slot];
+                    const Quad<T> qz = wc.z[slot], qm = wc.m[slot];
+                    const T old[8] = {qz.v[0], qz.v[1], qz.v[2], qz.v[3], qm.v[0], qm.v[1], qm.v[2], qm.v[3]};
                     scatter_corners(gmap, on_map_corners(cur, H, W), old);
                 }
             }

@@ -70,6 +70,12 @@ template <> struct Mth<float> {
     static __device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
     static __device__ __forceinline__ float to_cells(float x, float d_max, float res, float inv_res) { return (x + d_max) * inv_res; }
     static __device__ __forceinline__ float sqrt_rn(float x) { return sqrtf(x); }
+    // (|v|, 1 / max(|v|, 1e-6)) from |v|^2 with one rsqrt (2 ulp)
+    static __device__ __forceinline__ void norm_and_inv(float sq, float* nrm, float* inv) {
+        const float r = rsqrt(fmaxf(sq, 1e-12f));
+        *nrm = sq * r;
+        *inv = r;
+    }
 };
 
 template <> struct Mth<double> {
@@ -82,6 +88,10 @@ template <> struct Mth<double> {
     static __device__ __forceinline__ double fmax_(double a, double b) { return ::fmax(a, b); }
     static __device__ __forceinline__ double to_cells(double x, double d_max, double res, double) { return (x + d_max) / res; }
     static __device__ __forceinline__ double sqrt_rn(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ void norm_and_inv(double sq, double* nrm, double* inv) {
+        *nrm = ::sqrt(sq);
+        *inv = 1.0 / ::fmax(*nrm, 1e-6);
+    }
 };
 
 template <typename T>
@@ -92,6 +102,42 @@ __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     return v;
+}
+
+// Sums v[0..8) over the warp; every lane ends with all eight totals.  Reduce-scatter (each butterfly stage
+// halves the number of live values per lane) followed by an all-gather: 17 shuffles + 14 selects + 9 adds
+// instead of 40 shuffles + 40 adds for eight independent butterflies.
+template <typename T>
+__device__ __forceinline__ void warp_sum8(T* v, int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    T w[4], u[2], t;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const T keep = b4 ? v[i + 4] : v[i], send = b4 ? v[i] : v[i + 4];
+        w[i] = keep + __shfl_xor_sync(kFull, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const T keep = b3 ? w[i + 2] : w[i], send = b3 ? w[i] : w[i + 2];
+        u[i] = keep + __shfl_xor_sync(kFull, send, 8);
+    }
+    {
+        const T keep = b2 ? u[1] : u[0], send = b2 ? u[0] : u[1];
+        t = keep + __shfl_xor_sync(kFull, send, 4);
+    }
+    t += __shfl_xor_sync(kFull, t, 2);
+    t += __shfl_xor_sync(kFull, t, 1);
+    // lane with (bit4, bit3, bit2) = (k>>2, k>>1, k) & 1 holds total k
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __shfl_sync(kFull, t, ((k >> 2) & 1) * 16 + ((k >> 1) & 1) * 8 + (k & 1) * 4);
+}
+
+// lane id through a volatile asm so that the compiler keeps it in a register instead of re-deriving it
+// from %tid.x (S2R has a long latency) all over the unrolled step loop
+__device__ __forceinline__ int lane_id() {
+    int l;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+    return l;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -233,8 +279,8 @@ __device__ __forceinline__ void sin_versin(T x, T* sn, T* vs) {
 // R <- R (I + K sin(th dt) + K K (1 - cos(th dt))),  K = [w]x / max(|w|, 1e-6)   (dphysics.py:290-324)
 template <typename T>
 __device__ __forceinline__ void rodrigues_right(T* R, const T* w, T dt) {
-    const T th = Mth<T>::sqrt_rn(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-    const T inv = (T)1 / Mth<T>::fmax_(th, (T)1e-6);
+    T th, inv;
+    Mth<T>::norm_and_inv(w[0] * w[0] + w[1] * w[1] + w[2] * w[2], &th, &inv);
     const T k0 = w[0] * inv, k1 = w[1] * inv, k2 = w[2] * inv;
     T sn, c1;
     sin_versin(th * dt, &sn, &c1);
@@ -274,8 +320,8 @@ __device__ __forceinline__ void make_frame(StepFrame<T>& f, const Body<T>& s, T 
     for (int i = 0; i < 3; ++i) { f.x[i] = s.x[i]; f.v[i] = s.v[i]; f.w[i] = s.w[i]; }
     f.ox = Mth<T>::to_cells(s.x[0], d_max, res, inv_res);
     f.oy = Mth<T>::to_cells(s.x[1], d_max, res, inv_res);
-    const T nn = Mth<T>::sqrt_rn(s.R[0] * s.R[0] + s.R[3] * s.R[3] + s.R[6] * s.R[6]);
-    const T inv = (T)1 / Mth<T>::fmax_(nn, (T)1e-6);
+    T nn, inv;
+    Mth<T>::norm_and_inv(s.R[0] * s.R[0] + s.R[3] * s.R[3] + s.R[6] * s.R[6], &nn, &inv);
     f.hd[0] = s.R[0] * inv; f.hd[1] = s.R[3] * inv; f.hd[2] = s.R[6] * inv;
     f.uv = uv; f.uw = uw;
 }

@@ -71,7 +71,7 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
     fill_point_table(tab, a, PPL * 32);
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
+    const int lane = lane_id();
     const int b = blockIdx.x * kFwdWarps + (threadIdx.x >> 5);
     if (b >= a.B) return;
     const int n_last = a.N - (PPL - 1) * 32;            // valid lanes of the last slot
@@ -249,12 +249,16 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
             __syncwarp();
             emit_rows(Fs_t, Ff_t, img_s, img_f, phase, (int)rowF, lane);
         }
+        {
+            T red[8] = {sum[0], sum[1], sum[2], sum[3], sum[4], sum[5], nf_sum, nf_sq};
+            warp_sum8(red, lane);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) sum[k] = warp_sum(sum[k]);
+            for (int k = 0; k < 6; ++k) sum[k] = red[k];
+            nf_sum = red[6]; nf_sq = red[7];
+        }
 
         if (COST) {
             // unbiased std over the N points of |F_spring|, then Welford over steps
-            nf_sum = warp_sum(nf_sum); nf_sq = warp_sum(nf_sq);
             const T mean = nf_sum / (T)a.N;
             T var = (nf_sq - nf_sum * mean) / (T)(a.N - 1);
             var = Mth<T>::fmax_(var, (T)0);
