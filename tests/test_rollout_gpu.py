@@ -400,3 +400,66 @@ def test_moving_flippers_fp64_match_oracle(variant):
     out, _ = sim(zk.unsqueeze(0), controls.to(DEV), joint_angles=torch.zeros_like(ja).to(DEV))
     out[0].sum().backward()
     assert torch.isfinite(zk.grad).all()
+
+
+def _custom_robot(n_points, seed=0):
+    """A DPhysConfig whose body is the first / a resampled subset of marv's contact points (exercises every
+    points-per-lane instantiation, ragged last slots and the TMA row-alignment phases)."""
+    from monoforce_b200 import DPhysConfig
+    from monoforce_b200.dphys_config import part_ids
+    cfg = DPhysConfig(robot="marv", grid_res=0.2)
+    g = torch.Generator().manual_seed(seed)
+    base = cfg.robot_points
+    idx = torch.randint(0, base.shape[0], (n_points,), generator=g) if n_points > base.shape[0] else torch.randperm(base.shape[0], generator=g)[:n_points]
+    pts = base[idx] + (0.01 * torch.randn(n_points, 3, generator=g) if n_points > base.shape[0] else 0)
+    cfg.robot_points = pts.contiguous()
+    cfg.driving_parts = [m[idx].clone() for m in cfg.driving_parts]
+    cfg.part_id = part_ids(cfg.driving_parts, n_points)
+    return cfg
+
+
+@pytest.mark.parametrize("n_points,B,T,variant", [
+    (1, 1, 1, "step"), (5, 3, 2, "step"), (31, 5, 3, "odeint"), (32, 2, 5, "step"), (33, 7, 7, "odeint"),
+    (64, 9, 6, "step"), (100, 4, 9, "step"), (161, 6, 5, "odeint"), (200, 3, 11, "step"), (256, 5, 4, "step"),
+])
+def test_ragged_sizes_fp64_forward_and_adjoint(n_points, B, T, variant):
+    """Edge sizes: 1..256 contact points (all PPL instantiations), batch not a multiple of the CTA size, horizons
+    that hit every 16-byte phase of the force rows; forward and gradients vs the fp64 oracle."""
+    from monoforce_b200 import DPhysics
+    from oracle import dphysics_oracle as O
+    dtype = torch.float64
+    cfg = _custom_robot(n_points, seed=n_points)
+    cfg.traj_sim_time, cfg.use_odeint = T * cfg.dt + 1e-9, variant == "odeint"
+    sim = DPhysics(cfg, device=DEV)
+    z, controls, fr, st = _random_case(cfg, B, T, 100 + n_points, dtype)
+    spec = make_spec(cfg)
+    zr, cr = z.clone().requires_grad_(True), controls.clone().requires_grad_(True)
+    rs, rf = O.rollout(spec, zr.unsqueeze(0).expand(B, -1, -1), cr, state=st, friction=fr.unsqueeze(0).expand(B, -1, -1),
+                       variant=variant, dtype=dtype)
+    (rs[0].pow(2).sum() + 1e-6 * rf[0].pow(2).sum() + rs[2].sum()).backward()
+    zk, ck = z.to(DEV).requires_grad_(True), controls.to(DEV).requires_grad_(True)
+    ks, kf = sim(zk.unsqueeze(0), ck, state=tuple(s.to(DEV) for s in st), friction=fr.to(DEV).unsqueeze(0))
+    (ks[0].pow(2).sum() + 1e-6 * kf[0].pow(2).sum() + ks[2].sum()).backward()
+    for a, b in zip(ks + kf, rs + rf):
+        assert a.shape == b.shape
+        assert rel_err(a, b) < 1e-8
+    assert rel_err(zk.grad, zr.grad) < 1e-6
+    assert rel_err(ck.grad, cr.grad, 1e-9) < 1e-6
+
+
+def test_fp32_ragged_sizes_forces_bit_pattern():
+    """fp32 rows leave through TMA bulk stores + scalar head/tail stores: every element of every row must be written
+    (no stale bytes) for all row phases; compare against the device's own no-TMA reference: the fp64 kernel."""
+    from monoforce_b200 import DPhysics
+    for n_points, B, T in ((7, 5, 9), (175, 3, 6), (223, 2, 5), (130, 4, 7)):
+        cfg = _custom_robot(n_points, seed=n_points + 1)
+        cfg.traj_sim_time, cfg.use_odeint = T * cfg.dt + 1e-9, False
+        sim = DPhysics(cfg, device=DEV)
+        z, controls, fr, st = _random_case(cfg, B, T, 7 + n_points, torch.float64, terrain="flat", with_fric=False)
+        with torch.no_grad():
+            _, f64 = sim(z.to(DEV).unsqueeze(0), controls.to(DEV), state=tuple(s.to(DEV) for s in st))
+            sentinel = torch.full((B, T, n_points, 3), float("nan"), device=DEV)      # poison recycled allocations
+            del sentinel
+            _, f32 = sim(z.float().to(DEV).unsqueeze(0), controls.float().to(DEV), state=tuple(s.float().to(DEV) for s in st))
+        assert torch.isfinite(f32[0]).all() and torch.isfinite(f32[1]).all()
+        assert rel_err(f32[0], f64[0]) < 1e-3 and rel_err(f32[1], f64[1], 1e-6) < 5e-3
