@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--traj-per-gpu", type=int, default=4096)
     ap.add_argument("--cpu-sample", type=int, default=64, help="trajectories per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-encoder", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -324,6 +325,34 @@ def main():
         except Exception:
             traffic = None
 
+    # ---- BASELINE config 4 in brief: terrain encoder (16 scenes x 4 cameras, lss_cfg.yaml sizes, eval fast path) ----
+    encoder = None
+    if rank == 0 and world == 1 and not args.no_encoder:
+        try:
+            from helpers_lss import default_cfg, make_inputs
+            from monoforce_b200 import LiftSplatShoot
+            gc, ac = default_cfg()
+            torch.manual_seed(0)
+            net = LiftSplatShoot(gc, ac).to(dev).eval()
+            net.fast_inference = True
+            enc_in = [t.to(dev) for t in make_inputs(gc, ac, 16, 0)]
+            with torch.no_grad():
+                for _ in range(3):
+                    net(*enc_in)
+                torch.cuda.synchronize()
+                g_a, g_b = ev(), ev()
+                g_a.record()
+                for _ in range(5):
+                    net(*enc_in)
+                g_b.record()
+                torch.cuda.synchronize()
+            enc_ms = g_a.elapsed_time(g_b) / 5
+            encoder = {"workload": "LiftSplatShoot forward, 16 scenes x 4 cams 256x416 -> 128x128 BEV, eval, "
+                                   "tcgen05 dense layers + fused lift-splat", "ms": enc_ms, "scenes_per_s": 16 / (enc_ms * 1e-3)}
+            del net, enc_in
+        except Exception as e:     # the encoder is an extra; never let it break the headline line
+            encoder = {"error": repr(e)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         Bc = args.cpu_sample
@@ -357,6 +386,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "cpu_baseline": cpu,
+            "encoder": encoder,
             "loss": float(loss.detach()),
         }
         print(json.dumps(line), flush=True)
