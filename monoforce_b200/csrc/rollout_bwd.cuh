@@ -35,6 +35,24 @@ template <typename T> struct Quad;                       // 4 scalars moved as o
 template <> struct __align__(16) Quad<float> { float v[4]; };
 template <> struct __align__(16) Quad<double> { double v[4]; };
 
+__device__ __forceinline__ Quad<float> quad_load(const Quad<float>* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);       // one LDS.128
+    Quad<float> q; q.v[0] = t.x; q.v[1] = t.y; q.v[2] = t.z; q.v[3] = t.w;
+    return q;
+}
+__device__ __forceinline__ void quad_store(Quad<float>* p, const Quad<float>& q) {
+    *reinterpret_cast<float4*>(p) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]);      // one STS.128
+}
+__device__ __forceinline__ Quad<double> quad_load(const Quad<double>* p) {
+    const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+    Quad<double> q; q.v[0] = a.x; q.v[1] = a.y; q.v[2] = b.x; q.v[3] = b.y;
+    return q;
+}
+__device__ __forceinline__ void quad_store(Quad<double>* p, const Quad<double>& q) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(q.v[0], q.v[1]);
+    reinterpret_cast<double2*>(p)[1] = make_double2(q.v[2], q.v[3]);
+}
+
 template <typename T>
 struct MapGradCache {
     Quad<T> z[kMaxPointsPerLane * 32];               // d/dz of the point's current cell corners (00, 10, 01, 11)
@@ -446,7 +464,7 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                                  mu_b * w00, mu_b * w10, mu_b * w01, mu_b * w11};
                 if (e.cell >= 0) {
                     const int cur = wc.cell[slot];
-                    Quad<T> qz = wc.z[slot], qm = wc.m[slot];
+                    Quad<T> qz = quad_load(&wc.z[slot]), qm = quad_load(&wc.m[slot]);
                     if (cur == e.cell) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) { qz.v[k] += cg[k]; qm.v[k] += cg[4 + k]; }
@@ -459,7 +477,7 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) { qz.v[k] = cg[k]; qm.v[k] = cg[4 + k]; }
                     }
-                    wc.z[slot] = qz; wc.m[slot] = qm;
+                    quad_store(&wc.z[slot], qz); quad_store(&wc.m[slot], qm);
                 } else {
                     const T ggx = e.r[0] * a.inv_res + f.ox, ggy = e.r[1] * a.inv_res + f.oy;
                     scatter_corners(gmap, flat_corners((long long)ggx, (long long)ggy, H, W), cg);
@@ -553,7 +571,7 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                 const int slot = j * 32 + lane;
                 const int cur = wc.cell[slot];
                 if (cur >= 0) {
-                    const Quad<T> qz = wc.z[slot], qm = wc.m[slot];
+                    const Quad<T> qz = quad_load(&wc.z[slot]), qm = quad_load(&wc.m[slot]);
                     const T old[8] = {qz.v[0], qz.v[1], qz.v[2], qz.v[3], qm.v[0], qm.v[1], qm.v[2], qm.v[3]};
                     scatter_corners(gmap, on_map_corners(cur, H, W), old);
                 }

@@ -1,0 +1,34 @@
+"""Tiny workload for compute-sanitizer (memcheck / racecheck / synccheck): every kernel once, small sizes."""
+import os, sys
+_R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [_R, os.path.join(_R, "tests")]
+import torch
+from monoforce_b200 import DPhysics, DPhysConfig, LiftSplatShoot, ops
+from helpers_lss import small_cfg, make_inputs
+dev = "cuda"
+for robot, variant in (("marv", False), ("tradr", True)):
+    cfg = DPhysConfig(robot=robot, grid_res=0.4); cfg.traj_sim_time, cfg.use_odeint = 0.07, variant
+    sim = DPhysics(cfg, device=dev); sim.fused_cost = not variant
+    B, T = 5, 7
+    g = torch.Generator().manual_seed(0)
+    z = (0.1 * torch.randn(32, 32, generator=g)).to(dev).requires_grad_(True)
+    fr = (0.5 + 0.5 * torch.rand(32, 32, generator=g)).to(dev).requires_grad_(True)
+    c = (torch.rand(B, T, 2, generator=g) * 2 - 1).to(dev).requires_grad_(True)
+    x0 = torch.zeros(B, 3, device=dev); x0[0, 0] = 6.5; x0[1, 1] = -6.6     # two robots partly off the map
+    st = (x0, torch.zeros(B, 3, device=dev), torch.eye(3, device=dev).repeat(B, 1, 1), torch.zeros(B, 3, device=dev))
+    (Xs, Xd, Rs, Om), (Fs, Ff) = sim(z.unsqueeze(0), c, state=st, friction=fr.unsqueeze(0))
+    (Xs.sum() + Rs.sum() + 1e-3 * Fs.sum() + 1e-3 * Ff.sum()).backward()
+    if robot == "marv":
+        with torch.no_grad():
+            sim(z.detach().unsqueeze(0), c.detach(), joint_angles=torch.full((B, T, 4), 0.3, device=dev))
+grid_conf, aug_conf = small_cfg()
+torch.manual_seed(0)
+net = LiftSplatShoot(grid_conf, aug_conf).to(dev).eval()
+inp = [t.to(dev) for t in make_inputs(grid_conf, aug_conf, 1, 0)]
+x = inp[0].clone().requires_grad_(True)
+net(x, *inp[1:])["terrain"].sum().backward()
+with torch.no_grad():
+    net.fast_inference = True
+    net(*inp)
+torch.cuda.synchronize()
+print("sanitize target done")
