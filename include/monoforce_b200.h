@@ -71,7 +71,7 @@ typedef struct mfb_rollout_buffers {
     const int32_t* part_id; /* (N,)     driving part of each point or -1              */
     const void* ts;         /* (T,)     solver time grid; required for MFB_ODEINT_EULER, else may be NULL */
     const void* joint_angles; /* (B, T, 4) flipper angles of the 4 driving parts, or NULL for static geometry
-                               (DPhysics.update_joints, dphysics.py:326-358; forward only) */
+                               (DPhysics.update_joints, dphysics.py:326-358) */
     /* outputs */
     void* Xs;               /* (B, T, 3)                                              */
     void* Xds;              /* (B, T, 3)                                              */
@@ -106,6 +106,7 @@ typedef struct mfb_rollout_grads {
     void* g_xd0;              /* (B, 3)         */
     void* g_R0;               /* (B, 3, 3)      */
     void* g_omega0;           /* (B, 3)         */
+    void* g_joint_angles;     /* (B, T, 4) only with io->joint_angles (moving flippers) */
 } mfb_rollout_grads;
 
 /* ---- device-pointer entry points (asynchronous on `stream`, a cudaStream_t) ------------ */

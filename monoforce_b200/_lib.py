@@ -44,7 +44,7 @@ class RolloutBuffers(C.Structure):
 
 
 _GIN = ("g_Xs", "g_Xds", "g_Rs", "g_Omegas", "g_F_springs", "g_F_frictions", "g_x0z")
-_GOUT = ("g_z_grid", "g_friction", "g_controls", "g_x0", "g_xd0", "g_R0", "g_omega0")
+_GOUT = ("g_z_grid", "g_friction", "g_controls", "g_x0", "g_xd0", "g_R0", "g_omega0", "g_joint_angles")
 
 
 class RolloutGrads(C.Structure):

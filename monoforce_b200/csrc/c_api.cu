@@ -131,8 +131,6 @@ template <typename T>
 static int backward_typed(const mfb_rollout_desc& d, const mfb_rollout_buffers& io, const mfb_rollout_grads& g,
                           cudaStream_t st) {
     RolloutArgs<T> a = make_args<T>(d, io);
-    if (a.joint_angles)
-        return fail(MFB_ERR_UNSUPPORTED, "the adjoint of the moving-flipper variant (joint_angles != NULL) is not implemented");
     if (int rc = build_table<T>(d, io, st)) return rc;
     AdjointArgs<T> ga;
     ga.g_Xs = (const T*)g.g_Xs; ga.g_Xds = (const T*)g.g_Xds; ga.g_Rs = (const T*)g.g_Rs; ga.g_Oms = (const T*)g.g_Omegas;
@@ -150,6 +148,7 @@ static int backward_typed(const mfb_rollout_desc& d, const mfb_rollout_buffers& 
         if (me != cudaSuccess) return fail(MFB_ERR_CUDA, std::string("memset grad scratch: ") + cudaGetErrorString(me));
     }
     ga.g_controls = (T*)g.g_controls;
+    ga.g_joint_angles = (T*)g.g_joint_angles;
     ga.g_x0 = (T*)g.g_x0; ga.g_xd0 = (T*)g.g_xd0; ga.g_R0 = (T*)g.g_R0; ga.g_om0 = (T*)g.g_omega0;
     LaunchError e = d.variant == MFB_STEP_LOOP ? launch_rollout_bwd<T, kStepLoop>(a, ga, st)
                                                : launch_rollout_bwd<T, kOdeintEuler>(a, ga, st);

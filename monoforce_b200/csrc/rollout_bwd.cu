@@ -21,6 +21,7 @@ static LaunchError launch_ppl(const RolloutArgs<T>& a, const AdjointArgs<T>& g, 
         count_launch();
         return {nullptr};
     };
+    if (a.joint_angles) return go(rollout_bwd_kernel<T, PPL, VARIANT, true, true>);     // moving flippers
     if (g.g_Fs || g.g_Ff) return go(rollout_bwd_kernel<T, PPL, VARIANT, true>);
     return go(rollout_bwd_kernel<T, PPL, VARIANT, false>);
 }

@@ -128,7 +128,7 @@ __device__ __forceinline__ void rodrigues_right_bwd(const T* w, T dt, const T* E
     }
 }
 
-template <typename T, int PPL, int VARIANT, bool HAS_FGRAD>
+template <typename T, int PPL, int VARIANT, bool HAS_FGRAD, bool JOINTS = false>
 __global__ void __launch_bounds__(kBwdWarps * 32, (sizeof(T) == 4 && PPL <= 7) ? MFB_BWD_MINB : 1)
 rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
     __shared__ PointTable<T> tab;
@@ -220,6 +220,9 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
         g.g_controls[((long long)b * a.nT + a.nT - 1) * 2 + 1] = (T)0;
     }
 
+    if (JOINTS && VARIANT == kOdeintEuler && g.g_joint_angles && lane < 4)
+        g.g_joint_angles[((long long)b * a.nT + a.nT - 1) * 4 + lane] = (T)0;
+
     T w_post[3] = {0, 0, 0};     // angular velocity after step t (== pre-state of step t+1)
     if (n_steps > 0) {
         const int last = (VARIANT == kOdeintEuler) ? n_steps : n_steps - 1;
@@ -308,18 +311,12 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
 
         // ---------------- clamp mask of the angular acceleration ----------------
         // active  <=>  w' == fma(+-omega_max, h, w) bit-for-bit (the forward uses the same fma)
-        T tq_b[3];
-        {
-            T m[3];
+        T tq_b[3], wdm[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const bool hi = fma(a.omega_max, h, s.w[i]) == w_post[i];
-                const bool lo = fma(-a.omega_max, h, s.w[i]) == w_post[i];
-                m[i] = (hi || lo) ? (T)0 : wd_b[i];
-            }
-            // tq_bar = Iinv^T m
-#pragma unroll
-            for (int c = 0; c < 3; ++c) tq_b[c] = a.Iinv[0 + c] * m[0] + a.Iinv[3 + c] * m[1] + a.Iinv[6 + c] * m[2];
+        for (int i = 0; i < 3; ++i) {
+            const bool hi = fma(a.omega_max, h, s.w[i]) == w_post[i];
+            const bool lo = fma(-a.omega_max, h, s.w[i]) == w_post[i];
+            wdm[i] = (hi || lo) ? (T)0 : wd_b[i];
         }
         const T fs_b0 = vd_b[0] * a.inv_mass, fs_b1 = vd_b[1] * a.inv_mass, fs_b2 = vd_b[2] * a.inv_mass;
 
@@ -330,23 +327,53 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
         // ---------------- pass A: phase 1 forward ----------------
         T nrm[PPL][3], sc[PPL], slip[PPL][3], arm[PPL][3];
         T C = (T)0;
+        // moving flippers: lane i < 4 owns (cos, sin) of joint angle i; second moments of the articulated body
+        T jc = (T)1, js = (T)0, mom[6] = {0, 0, 0, 0, 0, 0};
+        if (JOINTS) {
+            const T ang = lane < 4 ? a.joint_angles[((long long)b * a.nT + t) * 4 + lane] : (T)0;
+            Mth<T>::sincos(ang, &js, &jc);
+        }
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
             const int slot = j * 32 + lane;
+            T px = tab.px[slot], py = tab.py[slot], pz = tab.pz[slot];
+            if (JOINTS) {
+                articulate_point(px, py, pz, tab.part[slot], jc, js, a.joint_pos);
+                if ((j < PPL - 1) || last_valid) {
+                    mom[0] += py * py + pz * pz; mom[1] += px * px + pz * pz; mom[2] += px * px + py * py;
+                    mom[3] += px * py; mom[4] += px * pz; mom[5] += py * pz;
+                }
+            }
             PointEval<T> e;
-            eval_point(e, f, tab.px[slot], tab.py[slot], tab.pz[slot], tab.driven[slot], tab.side[slot],
+            eval_point(e, f, px, py, pz, tab.driven[slot], tab.side[slot],
                        (j < PPL - 1) || last_valid, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
             C += e.cw;
             sc[j] = e.sp * e.cw;
 #pragma unroll
             for (int k = 0; k < 3; ++k) { slip[j][k] = e.sl[k]; nrm[j][k] = e.rec[4 + k]; arm[j][k] = e.r[k]; }
         }
-        C = warp_sum(C);
+        T Iinv[9];
+        if (JOINTS) {
+            T red[8] = {C, mom[0], mom[1], mom[2], mom[3], mom[4], mom[5], (T)0};
+            warp_sum8(red, lane);
+            C = red[0];
+            const T mp = a.mass / (T)a.N;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) mom[k] = red[1 + k] * mp;
+            invert_inertia(mom, Iinv);
+        } else {
+            C = warp_sum(C);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Iinv[k] = a.Iinv[k];
+        }
         const T invC = Mth<T>::rcp(C);
+        // tq_bar = Iinv^T (masked wd_bar)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) tq_b[c] = Iinv[0 + c] * wdm[0] + Iinv[3 + c] * wdm[1] + Iinv[6 + c] * wdm[2];
 
         // ---------------- pass B: phase 2 forward + its reverse ----------------
         // reuses the per-point registers: nrm -> G_bar, slip -> slip_bar, arm -> arm_bar
-        T Cb_part = (T)0;
+        T Cb_part = (T)0, tq_p[3] = {0, 0, 0};
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
             const T f = sc[j] * invC;
@@ -382,6 +409,9 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                     Ftb0 += e[3]; Ftb1 += e[4]; Ftb2 += e[5];
                 }
             }
+            if (JOINTS) {      // forward torque, needed for d wd / d Iinv
+                tq_p[0] += r1 * F2 - r2 * F1; tq_p[1] += r2 * F0 - r0 * F2; tq_p[2] += r0 * F1 - r1 * F0;
+            }
             arm[j][0] = F1 * tq_b[2] - F2 * tq_b[1];
             arm[j][1] = F2 * tq_b[0] - F0 * tq_b[2];
             arm[j][2] = F0 * tq_b[1] - F1 * tq_b[0];
@@ -400,18 +430,39 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             Cb_part += f_b * f;
             nrm[j][0] = Gb0; nrm[j][1] = Gb1; nrm[j][2] = Gb2;
         }
-        const T C_b = -warp_sum(Cb_part) * invC;
+        T C_b, mom_b[6] = {0, 0, 0, 0, 0, 0};
+        if (JOINTS) {
+            T red[8] = {Cb_part, tq_p[0], tq_p[1], tq_p[2], (T)0, (T)0, (T)0, (T)0};
+            warp_sum8(red, lane);
+            C_b = -red[0] * invC;
+            // wd = clamp(Iinv tq):  Iinv_bar = m tq^T  ->  I_bar = -Iinv^T Iinv_bar Iinv^T = -(tq_bar)(Iinv tq)^T
+            T u[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) u[r] = Iinv[r * 3 + 0] * red[1] + Iinv[r * 3 + 1] * red[2] + Iinv[r * 3 + 2] * red[3];
+            const T mp = a.mass / (T)a.N;
+            // I = mp [[m0, -m3, -m4], [-m3, m1, -m5], [-m4, -m5, m2]]
+            mom_b[0] = -mp * tq_b[0] * u[0];
+            mom_b[1] = -mp * tq_b[1] * u[1];
+            mom_b[2] = -mp * tq_b[2] * u[2];
+            mom_b[3] = mp * (tq_b[0] * u[1] + tq_b[1] * u[0]);
+            mom_b[4] = mp * (tq_b[0] * u[2] + tq_b[2] * u[0]);
+            mom_b[5] = mp * (tq_b[1] * u[2] + tq_b[2] * u[1]);
+        } else {
+            C_b = -warp_sum(Cb_part) * invC;
+        }
 
         // ---------------- pass C: phase 1 again, reversed ----------------
         T acc[24];
 #pragma unroll
         for (int k = 0; k < 24; ++k) acc[k] = (T)0;
         // acc: 0-2 x_bar, 3-5 v_bar, 6-8 w_bar, 9-17 R_bar, 18-20 hd_bar, 21-22 controls
+        T jg[4] = {0, 0, 0, 0};      // d loss / d joint angle, per driving part
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
             const int slot = j * 32 + lane;
             const bool ok = (j < PPL - 1 || last_valid);
-            const T px = tab.px[slot], py = tab.py[slot], pz = tab.pz[slot];
+            T px = tab.px[slot], py = tab.py[slot], pz = tab.pz[slot];
+            if (JOINTS) articulate_point(px, py, pz, tab.part[slot], jc, js, a.joint_pos);
             const T drv = tab.driven[slot], side = tab.side[slot];
             PointEval<T> e;
             eval_point(e, f, px, py, pz, drv, side, ok, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
@@ -498,8 +549,27 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             acc[9] += rb0 * px;  acc[10] += rb0 * py; acc[11] += rb0 * pz;
             acc[12] += rb1 * px; acc[13] += rb1 * py; acc[14] += rb1 * pz;
             acc[15] += rb2 * px; acc[16] += rb2 * py; acc[17] += rb2 * pz;
+            if (JOINTS) {
+                const int part = tab.part[slot];
+                if (ok && part >= 0) {
+                    // p'_bar = R^T r_bar + d(inertia moments)/dp' ; angle_bar += p'_bar . dp'/dangle
+                    const T pbx = s.R[0] * rb0 + s.R[3] * rb1 + s.R[6] * rb2 +
+                                  (T)2 * px * (mom_b[1] + mom_b[2]) + mom_b[3] * py + mom_b[4] * pz;
+                    const T pbz = s.R[2] * rb0 + s.R[5] * rb1 + s.R[8] * rb2 +
+                                  (T)2 * pz * (mom_b[0] + mom_b[1]) + mom_b[4] * px + mom_b[5] * py;
+                    const T ga = pbx * (pz - a.joint_pos[part * 3 + 2]) - pbz * (px - a.joint_pos[part * 3 + 0]);
+                    jg[0] += part == 0 ? ga : (T)0; jg[1] += part == 1 ? ga : (T)0;
+                    jg[2] += part == 2 ? ga : (T)0; jg[3] += part == 3 ? ga : (T)0;
+                }
+            }
         }
         warp_sum8(acc, lane); warp_sum8(acc + 8, lane); warp_sum8(acc + 16, lane);
+        if (JOINTS) {
+            T red[8] = {jg[0], jg[1], jg[2], jg[3], (T)0, (T)0, (T)0, (T)0};
+            warp_sum8(red, lane);
+            if (g.g_joint_angles && lane < 4)
+                g.g_joint_angles[((long long)b * a.nT + t) * 4 + lane] = lane == 0 ? red[0] : lane == 1 ? red[1] : lane == 2 ? red[2] : red[3];
+        }
 
         // fold the per-point sums into the state adjoint (pre-update state)
 #pragma unroll

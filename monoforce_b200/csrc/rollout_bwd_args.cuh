@@ -20,6 +20,7 @@ struct AdjointArgs {
                          // nullptr == no map gradient wanted
     long long g_maps_stride;   // elements between two trajectories' scratch maps (0 = shared)
     T* g_controls;       // (B,T,2)
+    T* g_joint_angles;   // (B,T,4) moving-flipper variant only
     T* g_x0;             // (B,3)
     T* g_xd0;            // (B,3)
     T* g_R0;             // (B,9)

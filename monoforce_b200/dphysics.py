@@ -96,8 +96,7 @@ def _ptr(t):
 
 class _RolloutMeta:
     """Everything that is not a differentiable tensor."""
-    __slots__ = ("desc", "points", "part_id", "ts", "want_forces", "want_cost", "dtype_code", "B", "T", "N", "timings",
-                 "joint_angles")
+    __slots__ = ("desc", "points", "part_id", "ts", "want_forces", "want_cost", "dtype_code", "B", "T", "N", "timings")
 
 
 def _require_cuda(*tensors):
@@ -127,7 +126,7 @@ def _workspace(lib, meta, dev):
 
 class _Rollout(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, mu, controls, x0, xd0, R0, om0, meta: _RolloutMeta):
+    def forward(ctx, z, mu, controls, x0, xd0, R0, om0, joint_angles, meta: _RolloutMeta):
         lib = _lib.load()
         dt_ = z.dtype
         dev = z.device
@@ -146,7 +145,7 @@ class _Rollout(torch.autograd.Function):
             workspace=_ptr(ws), workspace_bytes=ws.numel(),
             z_grid=_ptr(z), friction=_ptr(mu), controls=_ptr(controls), x0=_ptr(x0), xd0=_ptr(xd0), R0=_ptr(R0),
             omega0=_ptr(om0), points=_ptr(meta.points), part_id=_ptr(meta.part_id), ts=_ptr(meta.ts),
-            joint_angles=_ptr(meta.joint_angles),
+            joint_angles=_ptr(joint_angles),
             Xs=_ptr(Xs), Xds=_ptr(Xds), Rs=_ptr(Rs), Omegas=_ptr(Oms), F_springs=_ptr(Fs), F_frictions=_ptr(Ff),
             x0z=_ptr(x0z), cost=_ptr(cost))
         with torch.cuda.device(dev):
@@ -159,6 +158,7 @@ class _Rollout(torch.autograd.Function):
         ctx.meta = meta
         ctx.set_materialize_grads(False)     # unused outputs (e.g. the 2 x (B,T,N,3) forces) give None, not zeros
         ctx.save_for_backward(z, mu, controls, x0, xd0, R0, om0, Xs, Xds, Rs, Oms, x0z)
+        ctx.joint_angles = joint_angles
         empty = torch.empty(0, dtype=dt_, device=dev)
         outs = (Xs, Xds, Rs, Oms, Fs if Fs is not None else empty, Ff if Ff is not None else empty, x0z,
                 cost if cost is not None else empty)
@@ -185,19 +185,21 @@ class _Rollout(torch.autograd.Function):
         g_xd0 = torch.empty_like(xd0) if need[4] else None
         g_R0 = torch.empty_like(R0) if need[5] else None
         g_om0 = torch.empty_like(om0) if need[6] else None
+        ja = ctx.joint_angles
+        g_ja = torch.empty_like(ja) if (ja is not None and need[7]) else None
         ws = _workspace(lib, meta, dev)
         io = _lib.RolloutBuffers(
             workspace=_ptr(ws), workspace_bytes=ws.numel(),
             z_grid=_ptr(z), friction=_ptr(mu), controls=_ptr(controls), x0=_ptr(x0), xd0=_ptr(xd0), R0=_ptr(R0),
             omega0=_ptr(om0), points=_ptr(meta.points), part_id=_ptr(meta.part_id), ts=_ptr(meta.ts),
-            joint_angles=_ptr(meta.joint_angles),
+            joint_angles=_ptr(ja),
             Xs=_ptr(Xs), Xds=_ptr(Xds), Rs=_ptr(Rs), Omegas=_ptr(Oms), F_springs=None, F_frictions=None,
             x0z=_ptr(x0z), cost=None)
         grads = _lib.RolloutGrads(
             g_Xs=_ptr(gXs), g_Xds=_ptr(gXds), g_Rs=_ptr(gRs), g_Omegas=_ptr(gOms), g_F_springs=_ptr(gFs),
             g_F_frictions=_ptr(gFf), g_x0z=_ptr(gx0z),
             g_z_grid=_ptr(g_z), g_friction=_ptr(g_mu), g_controls=_ptr(g_c), g_x0=_ptr(g_x0), g_xd0=_ptr(g_xd0),
-            g_R0=_ptr(g_R0), g_omega0=_ptr(g_om0))
+            g_R0=_ptr(g_R0), g_omega0=_ptr(g_om0), g_joint_angles=_ptr(g_ja))
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             ev = _events(meta, "backward")
@@ -205,7 +207,7 @@ class _Rollout(torch.autograd.Function):
                                                 C.c_void_p(stream)), "mfb_rollout_backward")
             if ev is not None:
                 ev[2].record()
-        return g_z, g_mu, g_c, g_x0, g_xd0, g_R0, g_om0, None
+        return g_z, g_mu, g_c, g_x0, g_xd0, g_R0, g_om0, g_ja, None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -304,7 +306,7 @@ class DPhysics(torch.nn.Module):
                 ts = torch.linspace(0, cfg.traj_sim_time, n_full, dtype=dtype)[:T]
             meta.ts = ts.to(device=dev).contiguous()
         moving = self._moving_joints
-        meta.joint_angles = self.joint_angles.to(device=dev, dtype=dtype).contiguous() if moving else None
+        joint_angles = self.joint_angles.to(device=dev, dtype=dtype).contiguous() if moving else None
         meta.want_forces = bool(self.return_forces) or moving
         meta.want_cost = bool(self.fused_cost) and variant == _lib.MFB_STEP_LOOP and not moving
         meta.dtype_code = _lib.MFB_F32 if dtype == torch.float32 else _lib.MFB_F64
@@ -312,7 +314,7 @@ class DPhysics(torch.nn.Module):
         meta.timings = self.timings
         cast = lambda t: t.to(device=dev, dtype=dtype)
         Xs, Xds, Rs, Oms, Fs, Ff, x0z, cost = _Rollout.apply(cast(z), cast(mu), controls, cast(x0), cast(xd0),
-                                                              cast(R0), cast(om0), meta)
+                                                              cast(R0), cast(om0), joint_angles, meta)
         self._x0z = x0z
         self.last_cost = cost if meta.want_cost else None
         return Xs, Xds, Rs, Oms, Fs, Ff
@@ -367,11 +369,6 @@ class DPhysics(torch.nn.Module):
             # the reference articulates the body only for marv with non-zero angles (:340; one host sync per CALL
             # here instead of one per step there)
             self._moving_joints = cfg.robot == 'marv' and bool(torch.any(joint_angles != 0))
-            if self._moving_joints and (torch.is_grad_enabled() and any(
-                    t is not None and t.requires_grad for t in (z_grid, friction, controls, joint_angles, *state))):
-                raise NotImplementedError(
-                    "gradients through the moving-flipper variant (non-zero joint_angles on marv, dphysics.py:326-358) "
-                    "are not implemented; run it under torch.no_grad()")
         self.joint_angles = joint_angles if joint_angles is not None else \
             torch.zeros((B, N_ts, 4), device=self.device, dtype=dtype)
         self.ts = self.ts[:N_ts]                                                # :581

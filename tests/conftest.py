@@ -13,6 +13,11 @@ for p in (ROOT, HERE):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the C-ABI library is a build artefact (git-ignored): compile it once if a fresh checkout lacks it
+    from monoforce_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from monoforce_b200.build import build
+        build(verbose=True)
 
 
 def pytest_collection_modifyitems(config, items):

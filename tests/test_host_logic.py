@@ -29,7 +29,7 @@ def test_struct_layouts_match_header_sizes():
     # 8 int32 + int64 + 9 doubles + 9 doubles
     assert C.sizeof(_lib.RolloutDesc) == 8 * 4 + 8 + 9 * 8 + 9 * 8 + 12 * 8
     assert C.sizeof(_lib.RolloutBuffers) == 19 * 8 + 8 + 8
-    assert C.sizeof(_lib.RolloutGrads) == 14 * 8
+    assert C.sizeof(_lib.RolloutGrads) == 15 * 8
 
 
 def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():

@@ -393,13 +393,37 @@ def test_moving_flippers_fp64_match_oracle(variant):
         assert rel_err(a, b) < 1e-9
     for a, b in zip(kf, rf):
         assert rel_err(a, b) < 1e-8
-    # zero angles take the static-geometry kernel and gradients work; non-zero angles with grad are refused loudly
+    # zero angles take the static-geometry kernel
     zk = z.to(DEV).requires_grad_(True)
-    with pytest.raises(NotImplementedError):
-        sim(zk.unsqueeze(0), controls.to(DEV), joint_angles=ja.to(DEV))
     out, _ = sim(zk.unsqueeze(0), controls.to(DEV), joint_angles=torch.zeros_like(ja).to(DEV))
     out[0].sum().backward()
     assert torch.isfinite(zk.grad).all()
+
+
+@pytest.mark.parametrize("variant", ["step", "odeint"])
+def test_moving_flippers_adjoint_fp64_matches_oracle_autograd(variant):
+    """A8 + A11: gradients w.r.t. joint angles (through the articulated points AND the per-step inverse inertia),
+    height map, friction and controls vs autograd of the fp64 oracle."""
+    from oracle import dphysics_oracle as O
+    dtype = torch.float64
+    T, B = 25, 3
+    sim, cfg = _module("marv", 0.2, T, variant, dtype)
+    z, controls, fr, st = _random_case(cfg, B, T, 31, dtype)
+    gen = torch.Generator().manual_seed(5)
+    ja = 0.6 * torch.randn(B, T, 4, generator=gen, dtype=dtype)
+    spec = make_spec(cfg)
+    leaves_r = [t.clone().requires_grad_(True) for t in (z, fr, controls, ja)]
+    rs, rf = O.rollout(spec, leaves_r[0].unsqueeze(0).expand(B, -1, -1), leaves_r[2], joint_angles=leaves_r[3], state=st,
+                       friction=leaves_r[1].unsqueeze(0).expand(B, -1, -1), variant=variant, dtype=dtype)
+    wgt = torch.linspace(0.3, 1.0, T, dtype=dtype).view(1, T, 1)
+    ((rs[0] * wgt).pow(2).sum() + (rs[3] * wgt).sum() + 1e-6 * rf[0].pow(2).sum() + 1e-6 * rf[1].pow(2).sum()).backward()
+    leaves_k = [t.clone().to(DEV).requires_grad_(True) for t in (z, fr, controls, ja)]
+    ks, kf = sim(leaves_k[0].unsqueeze(0), leaves_k[2], joint_angles=leaves_k[3], state=tuple(s.to(DEV) for s in st),
+                 friction=leaves_k[1].unsqueeze(0))
+    w_d = wgt.to(DEV)
+    ((ks[0] * w_d).pow(2).sum() + (ks[3] * w_d).sum() + 1e-6 * kf[0].pow(2).sum() + 1e-6 * kf[1].pow(2).sum()).backward()
+    for name, a, b in zip(("z", "friction", "controls", "joint_angles"), leaves_k, leaves_r):
+        assert rel_err(a.grad, b.grad) < 1e-6, name
 
 
 def _custom_robot(n_points, seed=0):
