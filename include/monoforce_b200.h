@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MFB_ABI_VERSION 1
+#define MFB_ABI_VERSION 2
 
 typedef enum mfb_status {
     MFB_OK = 0,
@@ -81,6 +81,10 @@ typedef struct mfb_rollout_buffers {
     void* F_frictions;      /* (B, T, N, 3) or NULL (must be NULL iff F_springs is)   */
     void* x0z;              /* (B,)  start height written by the snap (dphysics.py:567-571) */
     void* cost;             /* (B,)  or NULL: std_t(std_p |F_spring|), step-loop variant only */
+    void* contact_sum;      /* (B, T) or NULL.  Adjoint tape: the forward writes the soft-contact normaliser
+                               sum_p sigmoid(-10 dh_p) of every step (dphysics.py:231), mfb_rollout_backward reads it
+                               back and then runs the single-sweep adjoint (each contact point visited once per
+                               step).  With NULL the backward recomputes it (three-pass adjoint, slower). */
     /* scratch */
     void* workspace;        /* device scratch of at least mfb_rollout_workspace_bytes(); holds the packed
                                per-cell sampling table the kernels build from z_grid / friction on every call */
@@ -112,7 +116,8 @@ typedef struct mfb_rollout_grads {
 /* ---- device-pointer entry points (asynchronous on `stream`, a cudaStream_t) ------------ */
 
 /* Bytes of device scratch mfb_rollout_forward / mfb_rollout_backward need for `desc` (16-byte
- * aligned base required): one 12-scalar record per map cell, per distinct map. */
+ * aligned base required): per distinct map and per cell one 12-scalar sampling record plus one
+ * 8-scalar corner-gradient record. */
 int64_t mfb_rollout_workspace_bytes(const mfb_rollout_desc* desc, int dtype);
 
 /* Replaces DPhysics.dphysics (dphysics.py:530-594): snap, T fused steps, post-processing. */
@@ -120,7 +125,8 @@ int mfb_rollout_forward(const mfb_rollout_desc* desc, const mfb_rollout_buffers*
                         int dtype, void* stream);
 
 /* Replaces autograd's backward through DPhysics.dphysics.  `io` must
- * hold the forward inputs and the recorded states (Xs, Xds, Rs, Omegas) of the same call. */
+ * hold the forward inputs and the recorded states (Xs, Xds, Rs, Omegas, x0z and, if it was
+ * requested, contact_sum) of the same call. */
 int mfb_rollout_backward(const mfb_rollout_desc* desc, const mfb_rollout_buffers* io,
                          const mfb_rollout_grads* grads, int dtype, void* stream);
 

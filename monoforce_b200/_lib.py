@@ -36,7 +36,7 @@ class RolloutDesc(C.Structure):
 
 
 _IN = ("z_grid", "friction", "controls", "x0", "xd0", "R0", "omega0", "points", "part_id", "ts", "joint_angles")
-_OUT = ("Xs", "Xds", "Rs", "Omegas", "F_springs", "F_frictions", "x0z", "cost")
+_OUT = ("Xs", "Xds", "Rs", "Omegas", "F_springs", "F_frictions", "x0z", "cost", "contact_sum")
 
 
 class RolloutBuffers(C.Structure):

@@ -68,6 +68,7 @@ static RolloutArgs<T> make_args(const mfb_rollout_desc& d, const mfb_rollout_buf
     a.cell_stride = d.map_stride == 0 ? 0 : (long long)d.H * d.W * kCellRec;
     a.Xs = (T*)io.Xs; a.Xds = (T*)io.Xds; a.Rs = (T*)io.Rs; a.Oms = (T*)io.Omegas;
     a.Fs = (T*)io.F_springs; a.Ff = (T*)io.F_frictions; a.x0z = (T*)io.x0z; a.cost = (T*)io.cost;
+    a.Csum = (T*)io.contact_sum;
     return a;
 }
 
@@ -83,14 +84,15 @@ static const char* check_io_forward(const mfb_rollout_desc& d, const mfb_rollout
     return nullptr;
 }
 
-// workspace layout: [cell table: n_maps*H*W*12 scalars][map-gradient scratch: n_maps*H*W*2 scalars]
+// workspace layout: [cell table: n_maps*H*W*12 scalars][map-gradient scratch: n_maps*H*W*8 scalars]
 static long long table_elems(const mfb_rollout_desc& d) {
     const long long n_maps = d.map_stride == 0 ? 1 : d.B;
     return n_maps * d.H * d.W * kCellRec;
 }
+constexpr int kGradScratchPerCell = 8;   // per-cell corner records of the single-sweep adjoint (the three-pass kernel uses 2)
 static long long workspace_bytes(const mfb_rollout_desc& d, int dtype) {
     const long long n_maps = d.map_stride == 0 ? 1 : d.B;
-    return (table_elems(d) + n_maps * d.H * d.W * 2) * (dtype == MFB_F32 ? 4 : 8);
+    return (table_elems(d) + n_maps * d.H * d.W * kGradScratchPerCell) * (dtype == MFB_F32 ? 4 : 8);
 }
 
 static const char* check_workspace(const mfb_rollout_desc& d, const mfb_rollout_buffers& io, int dtype) {
@@ -136,17 +138,16 @@ static int backward_typed(const mfb_rollout_desc& d, const mfb_rollout_buffers& 
     ga.g_Xs = (const T*)g.g_Xs; ga.g_Xds = (const T*)g.g_Xds; ga.g_Rs = (const T*)g.g_Rs; ga.g_Oms = (const T*)g.g_Omegas;
     ga.g_Fs = (const T*)g.g_F_springs; ga.g_Ff = (const T*)g.g_F_frictions; ga.g_x0z = (const T*)g.g_x0z;
     const long long n_maps = d.map_stride == 0 ? 1 : d.B;
-    const long long cells_total = n_maps * d.H * d.W;
     const bool want_maps = g.g_z_grid || g.g_friction;
     if (want_maps && d.map_stride != 0 && d.map_stride != (long long)d.H * d.W)
         return fail(MFB_ERR_UNSUPPORTED, "map gradients need densely packed per-trajectory maps (map_stride == H*W)");
     T* scratch = (T*)io.workspace + table_elems(d);
-    ga.g_maps = want_maps ? scratch : nullptr;
-    ga.g_maps_stride = d.map_stride == 0 ? 0 : (long long)d.H * d.W * 2;
-    if (want_maps) {
-        cudaError_t me = cudaMemsetAsync(scratch, 0, (size_t)cells_total * 2 * sizeof(T), st);
-        if (me != cudaSuccess) return fail(MFB_ERR_CUDA, std::string("memset grad scratch: ") + cudaGetErrorString(me));
-    }
+    ga.g_scratch = want_maps ? scratch : nullptr;
+    ga.n_maps = n_maps;
+    ga.g_maps = ga.g_cells = nullptr;
+    ga.g_maps_stride = ga.g_cells_stride = 0;
+    ga.g_z = (T*)g.g_z_grid; ga.g_mu = (T*)g.g_friction;
+    ga.g_dir_stride = d.map_stride == 0 ? 0 : (long long)d.H * d.W;
     ga.g_controls = (T*)g.g_controls;
     ga.g_joint_angles = (T*)g.g_joint_angles;
     ga.g_x0 = (T*)g.g_x0; ga.g_xd0 = (T*)g.g_xd0; ga.g_R0 = (T*)g.g_R0; ga.g_om0 = (T*)g.g_omega0;
@@ -155,11 +156,6 @@ static int backward_typed(const mfb_rollout_desc& d, const mfb_rollout_buffers& 
     if (e.msg) return fail(MFB_ERR_UNSUPPORTED, e.msg);
     cudaError_t ce = cudaGetLastError();
     if (ce != cudaSuccess) return fail(MFB_ERR_CUDA, std::string("rollout_bwd launch: ") + cudaGetErrorString(ce));
-    if (want_maps) {
-        launch_scatter_map_grads<T, kStepLoop>(scratch, (T*)g.g_z_grid, (T*)g.g_friction, cells_total, st);
-        ce = cudaGetLastError();
-        if (ce != cudaSuccess) return fail(MFB_ERR_CUDA, std::string("scatter_map_grads launch: ") + cudaGetErrorString(ce));
-    }
     return MFB_OK;
 }
 
@@ -266,6 +262,7 @@ int mfb_rollout_forward_host(const mfb_rollout_desc* desc, const mfb_rollout_buf
     dev.cost = io->cost ? base + s_cost.off : nullptr;
     dev.F_springs = forces ? base + s_Fs.off : nullptr;
     dev.F_frictions = forces ? base + s_Ff.off : nullptr;
+    dev.contact_sum = nullptr;                 // adjoint tape: not part of the host entry point
     dev.workspace = base + s_ws.off;
     dev.workspace_bytes = (int64_t)s_ws.bytes;
 

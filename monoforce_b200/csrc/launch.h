@@ -14,12 +14,10 @@ template <typename T, int VARIANT>
 LaunchError launch_rollout_fwd(const RolloutArgs<T>& args, cudaStream_t stream);
 
 template <typename T> struct AdjointArgs;
+// zeroes g.g_scratch, runs the adjoint kernel (single-sweep when the contact_sum tape is present and the geometry
+// is static, else the three-pass kernel) and adds the map-gradient scratch into g.g_z / g.g_mu
 template <typename T, int VARIANT>
 LaunchError launch_rollout_bwd(const RolloutArgs<T>& args, const AdjointArgs<T>& g, cudaStream_t stream);
-
-// adds the interleaved (z, mu) gradient scratch into the caller's maps (instantiated next to the kernels)
-template <typename T, int VARIANT>
-void launch_scatter_map_grads(const T* g2, T* g_z, T* g_mu, long long n, cudaStream_t stream);
 
 void count_launch();
 

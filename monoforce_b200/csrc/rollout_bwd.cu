@@ -1,7 +1,7 @@
 // Instantiations + PPL dispatcher of the adjoint rollout kernel (K2) for one
 // (scalar type, integrator variant) pair: -DMFB_INST_T=... -DMFB_INST_VARIANT=...
 #include "launch.h"
-#include "rollout_bwd.cuh"
+#include "rollout_bwd_sweep.cuh"
 
 #ifndef MFB_INST_T
 #error "compile with -DMFB_INST_T=float|double -DMFB_INST_VARIANT=0|1"
@@ -26,32 +26,70 @@ static LaunchError launch_ppl(const RolloutArgs<T>& a, const AdjointArgs<T>& g, 
     return go(rollout_bwd_kernel<T, PPL, VARIANT, false>);
 }
 
-template <>
-LaunchError launch_rollout_bwd<MFB_INST_T, MFB_INST_VARIANT>(const RolloutArgs<MFB_INST_T>& a,
-                                                            const AdjointArgs<MFB_INST_T>& g, cudaStream_t st) {
-    using T = MFB_INST_T;
-    constexpr int V = MFB_INST_VARIANT;
-    const int ppl = (a.N + 31) / 32;
-    switch (ppl) {
-        case 1: return launch_ppl<T, 1, V>(a, g, st);
-        case 2: return launch_ppl<T, 2, V>(a, g, st);
-        case 3: return launch_ppl<T, 3, V>(a, g, st);
-        case 4: return launch_ppl<T, 4, V>(a, g, st);
-        case 5: return launch_ppl<T, 5, V>(a, g, st);
-        case 6: return launch_ppl<T, 6, V>(a, g, st);
-        case 7: return launch_ppl<T, 7, V>(a, g, st);
-        case 8: return launch_ppl<T, 8, V>(a, g, st);
-        default: return {"number of contact points must be in [1, 256]"};
+// single-sweep adjoint (K2s): static geometry + the forward's contact_sum tape
+template <typename T, int VARIANT>
+static LaunchError launch_sweep(const RolloutArgs<T>& a, const AdjointArgs<T>& g, cudaStream_t st) {
+    const dim3 grid((a.B + kSweepWarps - 1) / kSweepWarps), block(kSweepWarps * 32);
+    const int slots = ((a.N + 31) / 32) * 32;
+    const size_t smem = g.g_cells ? (size_t)kSweepWarps * 3 * slots * sizeof(Quad<T>) : 0;
+    auto go = [&](auto kern) -> LaunchError {
+        if (smem > 0 &&
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return {"cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"};
+        kern<<<grid, block, smem, st>>>(a, g);
+        count_launch();
+        return {nullptr};
+    };
+    if constexpr (VARIANT == kStepLoop) {
+        if (g.g_Fs || g.g_Ff) return go(rollout_bwd_sweep_kernel<T, VARIANT, true>);
     }
+    return go(rollout_bwd_sweep_kernel<T, VARIANT, false>);
 }
 
 template <>
-void launch_scatter_map_grads<MFB_INST_T, MFB_INST_VARIANT>(const MFB_INST_T* g2, MFB_INST_T* g_z, MFB_INST_T* g_mu,
-                                                            long long n, cudaStream_t st) {
-    const int block = 256;
-    const int grid = (int)((n + block - 1) / block < 148 * 16 ? (n + block - 1) / block : 148 * 16);
-    scatter_map_grads_kernel<MFB_INST_T><<<grid, block, 0, st>>>(g2, g_z, g_mu, n);
-    count_launch();
+LaunchError launch_rollout_bwd<MFB_INST_T, MFB_INST_VARIANT>(const RolloutArgs<MFB_INST_T>& a,
+                                                            const AdjointArgs<MFB_INST_T>& g_in, cudaStream_t st) {
+    using T = MFB_INST_T;
+    constexpr int V = MFB_INST_VARIANT;
+    AdjointArgs<T> g = g_in;
+    const long long HW = (long long)a.H * a.W;
+    const bool shared_map = a.map_stride == 0;
+    const bool sweep = a.Csum != nullptr && a.joint_angles == nullptr && !(V == kOdeintEuler && (g.g_Fs || g.g_Ff));
+    const int per_cell = sweep ? kGradRec : 2;
+    g.g_maps = g.g_cells = nullptr;
+    if (g.g_scratch) {
+        if (cudaMemsetAsync(g.g_scratch, 0, (size_t)(g.n_maps * HW * per_cell) * sizeof(T), st) != cudaSuccess)
+            return {"cudaMemsetAsync(map-gradient scratch) failed"};
+        if (sweep) { g.g_cells = g.g_scratch; g.g_cells_stride = shared_map ? 0 : HW * kGradRec; }
+        else { g.g_maps = g.g_scratch; g.g_maps_stride = shared_map ? 0 : HW * 2; }
+    }
+    LaunchError e{nullptr};
+    if (sweep) {
+        e = launch_sweep<T, V>(a, g, st);
+    } else {
+        const int ppl = (a.N + 31) / 32;
+        switch (ppl) {
+            case 1: e = launch_ppl<T, 1, V>(a, g, st); break;
+            case 2: e = launch_ppl<T, 2, V>(a, g, st); break;
+            case 3: e = launch_ppl<T, 3, V>(a, g, st); break;
+            case 4: e = launch_ppl<T, 4, V>(a, g, st); break;
+            case 5: e = launch_ppl<T, 5, V>(a, g, st); break;
+            case 6: e = launch_ppl<T, 6, V>(a, g, st); break;
+            case 7: e = launch_ppl<T, 7, V>(a, g, st); break;
+            case 8: e = launch_ppl<T, 8, V>(a, g, st); break;
+            default: return {"number of contact points must be in [1, 256]"};
+        }
+    }
+    if (e.msg) return e;
+    if (g.g_scratch) {
+        const long long n = g.n_maps * HW;
+        const int block = 256;
+        const int grid = (int)((n + block - 1) / block < 148 * 16 ? (n + block - 1) / block : 148 * 16);
+        if (sweep) finalize_map_grads_kernel<T><<<grid, block, 0, st>>>(g.g_scratch, g.g_z, g.g_mu, (int)g.n_maps, a.H, a.W);
+        else scatter_map_grads_kernel<T><<<grid, block, 0, st>>>(g.g_scratch, g.g_z, g.g_mu, n);
+        count_launch();
+    }
+    return {nullptr};
 }
 
 }  // namespace mfb

@@ -49,6 +49,8 @@ struct RolloutArgs {
     T* Ff;                       // (B,T,N,3) or nullptr
     T* x0z;                      // (B,) snapped start height (dphysics.py:567-571)
     T* cost;                     // (B,) or nullptr: std_t(std_p |F_spring|), monoforce_node.py:91
+    T* Csum;                     // (B,T) or nullptr: soft-contact normaliser sum_p c_p of every step (dphysics.py:231), the
+                                 // tape the single-sweep adjoint reads back (written by the forward, read by the backward)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -59,6 +61,8 @@ template <typename T> struct Mth;
 template <> struct Mth<float> {
     static __device__ __forceinline__ float rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
     static __device__ __forceinline__ float rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    // reciprocal for warp-uniform scalars: SFU seed + one Newton step (<= 1 ulp), no IEEE slow path
+    static __device__ __forceinline__ float inv(float x) { const float y = rcp(x); return fmaf(fmaf(-x, y, 1.0f), y, y); }
     static __device__ __forceinline__ float sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
     // sigmoid(-10 dh) = 1 / (1 + exp(10 dh))
     static __device__ __forceinline__ float contact(float dh) {
@@ -81,6 +85,7 @@ template <> struct Mth<float> {
 template <> struct Mth<double> {
     static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
     static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+    static __device__ __forceinline__ double inv(double x) { return 1.0 / x; }
     static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
     static __device__ __forceinline__ double contact(double dh) { return 1.0 / (1.0 + ::exp(10.0 * dh)); }
     static __device__ __forceinline__ void sincos(double x, double* s, double* c) { ::sincos(x, s, c); }

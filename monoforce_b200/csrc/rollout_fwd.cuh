@@ -197,6 +197,7 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
 
         C = warp_sum(C);
         const T invC = Mth<T>::rcp(C);
+        if (a.Csum && lane == 0) a.Csum[(long long)b * a.nT + t] = C;      // tape of the single-sweep adjoint
 
         T sum[6];
 #pragma unroll

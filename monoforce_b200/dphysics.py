@@ -96,7 +96,8 @@ def _ptr(t):
 
 class _RolloutMeta:
     """Everything that is not a differentiable tensor."""
-    __slots__ = ("desc", "points", "part_id", "ts", "want_forces", "want_cost", "dtype_code", "B", "T", "N", "timings")
+    __slots__ = ("desc", "points", "part_id", "ts", "want_forces", "want_cost", "dtype_code", "B", "T", "N", "timings",
+                 "use_tape")
 
 
 def _require_cuda(*tensors):
@@ -140,6 +141,8 @@ class _Rollout(torch.autograd.Function):
         Ff = new(B, T, N, 3) if meta.want_forces else None
         x0z = new(B)
         cost = new(B) if meta.want_cost else None
+        # adjoint tape (4 bytes per trajectory-step): only when a backward can follow
+        csum = new(B, T) if meta.use_tape else None
         ws = _workspace(lib, meta, dev)
         io = _lib.RolloutBuffers(
             workspace=_ptr(ws), workspace_bytes=ws.numel(),
@@ -147,7 +150,7 @@ class _Rollout(torch.autograd.Function):
             omega0=_ptr(om0), points=_ptr(meta.points), part_id=_ptr(meta.part_id), ts=_ptr(meta.ts),
             joint_angles=_ptr(joint_angles),
             Xs=_ptr(Xs), Xds=_ptr(Xds), Rs=_ptr(Rs), Omegas=_ptr(Oms), F_springs=_ptr(Fs), F_frictions=_ptr(Ff),
-            x0z=_ptr(x0z), cost=_ptr(cost))
+            x0z=_ptr(x0z), cost=_ptr(cost), contact_sum=_ptr(csum))
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             ev = _events(meta, "forward")
@@ -159,6 +162,7 @@ class _Rollout(torch.autograd.Function):
         ctx.set_materialize_grads(False)     # unused outputs (e.g. the 2 x (B,T,N,3) forces) give None, not zeros
         ctx.save_for_backward(z, mu, controls, x0, xd0, R0, om0, Xs, Xds, Rs, Oms, x0z)
         ctx.joint_angles = joint_angles
+        ctx.csum = csum
         empty = torch.empty(0, dtype=dt_, device=dev)
         outs = (Xs, Xds, Rs, Oms, Fs if Fs is not None else empty, Ff if Ff is not None else empty, x0z,
                 cost if cost is not None else empty)
@@ -194,7 +198,7 @@ class _Rollout(torch.autograd.Function):
             omega0=_ptr(om0), points=_ptr(meta.points), part_id=_ptr(meta.part_id), ts=_ptr(meta.ts),
             joint_angles=_ptr(ja),
             Xs=_ptr(Xs), Xds=_ptr(Xds), Rs=_ptr(Rs), Omegas=_ptr(Oms), F_springs=None, F_frictions=None,
-            x0z=_ptr(x0z), cost=None)
+            x0z=_ptr(x0z), cost=None, contact_sum=_ptr(ctx.csum))
         grads = _lib.RolloutGrads(
             g_Xs=_ptr(gXs), g_Xds=_ptr(gXds), g_Rs=_ptr(gRs), g_Omegas=_ptr(gOms), g_F_springs=_ptr(gFs),
             g_F_frictions=_ptr(gFf), g_x0z=_ptr(gx0z),
@@ -222,6 +226,8 @@ class DPhysics(torch.nn.Module):
       * ``fused_cost`` (False): when True the kernel also emits the per-trajectory traversal
         cost ``norm(F_springs).std(-1).std(-1)`` (monoforce_node.py:91) in ``last_cost``.
       * ``timings`` (None): set to a list to collect CUDA events around each library call.
+      * ``adjoint_tape`` (True): record the per-step soft-contact normaliser (4 B per trajectory-step) when
+        gradients are required, which lets the backward run the single-sweep adjoint kernel.
     """
 
     def __init__(self, dphys_cfg=None, device='cpu'):
@@ -245,6 +251,7 @@ class DPhysics(torch.nn.Module):
         self.return_forces = True
         self.fused_cost = False
         self.last_cost = None
+        self.adjoint_tape = True  # False: no contact_sum tape, the backward runs the three-pass adjoint (development / tests)
         self.timings = None      # set to a list to collect (name, start_event, end_event) around every library call
         self._const_cache = {}
 
@@ -313,6 +320,9 @@ class DPhysics(torch.nn.Module):
         meta.B, meta.T, meta.N = B, T, pts.shape[0]
         meta.timings = self.timings
         cast = lambda t: t.to(device=dev, dtype=dtype)
+        # contact_sum tape for the single-sweep adjoint: only when a backward can follow this call
+        meta.use_tape = bool(self.adjoint_tape) and torch.is_grad_enabled() and any(
+            t is not None and t.requires_grad for t in (z, mu, controls, x0, xd0, R0, om0, joint_angles))
         Xs, Xds, Rs, Oms, Fs, Ff, x0z, cost = _Rollout.apply(cast(z), cast(mu), controls, cast(x0), cast(xd0),
                                                               cast(R0), cast(om0), joint_angles, meta)
         self._x0z = x0z

@@ -18,12 +18,32 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+ADJOINT_TAPE = True      # flipped by the `adjoint_kernel` fixture: single-sweep (tape) vs three-pass adjoint
+
+
+@pytest.fixture(params=["sweep", "three_pass"])
+def adjoint_kernel(request):
+    """Runs an adjoint test once per backward kernel: K2s (single sweep, reads the forward's contact_sum tape)
+    and K2 (three-pass, recomputes it)."""
+    global ADJOINT_TAPE
+    ADJOINT_TAPE = request.param == "sweep"
+    yield request.param
+    ADJOINT_TAPE = True
+
+
+def _sim(cfg):
+    from monoforce_b200 import DPhysics
+    sim = DPhysics(cfg, device=DEV)
+    sim.adjoint_tape = ADJOINT_TAPE
+    return sim
+
+
 def _module(robot, grid_res, T, variant="step", dtype=torch.float32):
-    from monoforce_b200 import DPhysics, DPhysConfig
+    from monoforce_b200 import DPhysConfig
     cfg = DPhysConfig(robot=robot, grid_res=grid_res)
     cfg.traj_sim_time = T * cfg.dt
     cfg.use_odeint = (variant == "odeint")
-    return DPhysics(cfg, device=DEV), cfg
+    return _sim(cfg), cfg
 
 
 def _t(a, dtype=torch.float32):
@@ -203,7 +223,7 @@ def test_fp32_rough_terrain_error_envelope():
 
 
 @pytest.mark.parametrize("name", ["grad64_marv_noise128_T40_B2", "grad64_tradr_noise64_T40_B2"])
-def test_fp64_adjoint_matches_reference_autograd(name):
+def test_fp64_adjoint_matches_reference_autograd(name, adjoint_kernel):
     """P4: hand-written adjoint == autograd of the unmodified reference (fp64 goldens)."""
     g = load_golden(name)
     dtype = torch.float64
@@ -227,7 +247,7 @@ def test_fp64_adjoint_matches_reference_autograd(name):
 
 
 @pytest.mark.parametrize("variant", ["step", "odeint"])
-def test_fp64_adjoint_matches_oracle_autograd(variant):
+def test_fp64_adjoint_matches_oracle_autograd(variant, adjoint_kernel):
     """P4 on a second objective (positions only, default initial state -> gradient reaches controls[:,0]
     through the initial velocity too), both integrator variants."""
     from oracle import dphysics_oracle as O
@@ -249,7 +269,7 @@ def test_fp64_adjoint_matches_oracle_autograd(variant):
     assert rel_err(ck.grad, cr.grad) < 1e-7
 
 
-def test_fp32_adjoint_close_to_fp64():
+def test_fp32_adjoint_close_to_fp64(adjoint_kernel):
     from oracle import dphysics_oracle as O
     T, B = 50, 4
     sim, cfg = _module("marv", 0.1, T)
@@ -285,6 +305,51 @@ def test_per_trajectory_maps_and_off_map_clamp():
     ks, kf = sim(z.to(DEV), controls.to(DEV), state=tuple(s.to(DEV) for s in st), friction=fr.to(DEV))
     for a, b in zip(ks + kf, rs + rf):
         assert rel_err(a, b) < 1e-8
+
+
+@pytest.mark.parametrize("variant", ["step", "odeint"])
+@pytest.mark.parametrize("shared", [False, True])
+def test_adjoint_off_map_and_per_trajectory_maps(variant, shared, adjoint_kernel):
+    """Gradients when contact points leave the map (the reference's clamped flat indices, dphysics.py:432-435) and
+    when every trajectory has its own map (the training path): d/dz_grid, d/dfriction, d/dcontrols and d/dstate
+    vs autograd of the fp64 oracle.  All output gradients are dense (states and both force tensors)."""
+    from oracle import dphysics_oracle as O
+    dtype = torch.float64
+    T, B = 25, 6
+    sim, cfg = _module("tradr", 0.4, T, variant, dtype)
+    gen = torch.Generator().manual_seed(14)
+    H = cfg.x_grid.shape[0]
+    nm = 1 if shared else B
+    z = 0.2 * torch.randn(nm, H, H, generator=gen, dtype=dtype)
+    fr = 0.3 + 0.7 * torch.rand(nm, H, H, generator=gen, dtype=dtype)
+    _, controls, _, st = _random_case(cfg, B, T, 19, dtype)
+    x = st[0].clone()
+    x[0, 0] = 6.9; x[1, 1] = -7.3; x[2, 0] = -6.45; x[3, :2] = torch.tensor([6.35, 6.38], dtype=dtype)
+    x[4, :2] = torch.tensor([-6.2, 6.3], dtype=dtype)
+    st = (x, st[1], st[2], st[3])
+    gw = [torch.randn(B, T, 3, generator=gen, dtype=dtype), torch.randn(B, T, 3, generator=gen, dtype=dtype),
+          torch.randn(B, T, 3, 3, generator=gen, dtype=dtype), torch.randn(B, T, 3, generator=gen, dtype=dtype)]
+    fw = 1e-3 * torch.randn(B, T, cfg.robot_points.shape[0], 3, generator=gen, dtype=dtype)
+
+    def objective(states, forces, dev):
+        l = sum((o * w.to(dev)).sum() for o, w in zip(states, gw))
+        return l + (forces[0] * fw.to(dev)).sum() + 0.5 * (forces[1] * fw.to(dev)).sum()
+
+    leaves_r = [t.clone().requires_grad_(True) for t in (z, fr, controls) + st]
+    zr, frr = leaves_r[0], leaves_r[1]
+    rs, rf = O.rollout(make_spec(cfg), zr.expand(B, -1, -1) if shared else zr, leaves_r[2],
+                       state=tuple(t * 1.0 for t in leaves_r[3:]), friction=frr.expand(B, -1, -1) if shared else frr,
+                       variant=variant, dtype=dtype)
+    objective(rs, rf, "cpu").backward()
+    leaves_k = [t.clone().to(DEV).requires_grad_(True) for t in (z, fr, controls) + st]
+    zk, frk = leaves_k[0], leaves_k[1]
+    ks, kf = sim(zk.expand(B, -1, -1) if shared else zk, leaves_k[2], state=tuple(t * 1.0 for t in leaves_k[3:]),
+                 friction=frk.expand(B, -1, -1) if shared else frk)
+    for a, b in zip(ks + kf, rs + rf):
+        assert rel_err(a, b) < 1e-8
+    objective(ks, kf, DEV).backward()
+    for name, a, b in zip(("z", "friction", "controls", "x0", "xd0", "R0", "om0"), leaves_k, leaves_r):
+        assert rel_err(a.grad, b.grad, 1e-9) < 1e-6, name
 
 
 def test_fused_cost_matches_torch_definition():
@@ -446,7 +511,7 @@ def _custom_robot(n_points, seed=0):
     (1, 1, 1, "step"), (5, 3, 2, "step"), (31, 5, 3, "odeint"), (32, 2, 5, "step"), (33, 7, 7, "odeint"),
     (64, 9, 6, "step"), (100, 4, 9, "step"), (161, 6, 5, "odeint"), (200, 3, 11, "step"), (256, 5, 4, "step"),
 ])
-def test_ragged_sizes_fp64_forward_and_adjoint(n_points, B, T, variant):
+def test_ragged_sizes_fp64_forward_and_adjoint(n_points, B, T, variant, adjoint_kernel):
     """Edge sizes: 1..256 contact points (all PPL instantiations), batch not a multiple of the CTA size, horizons
     that hit every 16-byte phase of the force rows; forward and gradients vs the fp64 oracle."""
     from monoforce_b200 import DPhysics
@@ -454,7 +519,7 @@ def test_ragged_sizes_fp64_forward_and_adjoint(n_points, B, T, variant):
     dtype = torch.float64
     cfg = _custom_robot(n_points, seed=n_points)
     cfg.traj_sim_time, cfg.use_odeint = T * cfg.dt + 1e-9, variant == "odeint"
-    sim = DPhysics(cfg, device=DEV)
+    sim = _sim(cfg)
     z, controls, fr, st = _random_case(cfg, B, T, 100 + n_points, dtype)
     spec = make_spec(cfg)
     zr, cr = z.clone().requires_grad_(True), controls.clone().requires_grad_(True)
