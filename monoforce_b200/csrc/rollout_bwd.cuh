@@ -31,28 +31,6 @@ constexpr int kBwdWarps = 4;
 // memory when the point moves to another cell: ~10x fewer global atomics than one per step.
 // The global target interleaves (d/dz, d/dfriction) per cell so a flush is two 16-byte or four
 // 8-byte vector reductions (red.global.add.v4.f32 / .v2.f32, sm_90+).
-template <typename T> struct Quad;                       // 4 scalars moved as one or two 16-byte shared accesses
-template <> struct __align__(16) Quad<float> { float v[4]; };
-template <> struct __align__(16) Quad<double> { double v[4]; };
-
-__device__ __forceinline__ Quad<float> quad_load(const Quad<float>* p) {
-    const float4 t = *reinterpret_cast<const float4*>(p);       // one LDS.128
-    Quad<float> q; q.v[0] = t.x; q.v[1] = t.y; q.v[2] = t.z; q.v[3] = t.w;
-    return q;
-}
-__device__ __forceinline__ void quad_store(Quad<float>* p, const Quad<float>& q) {
-    *reinterpret_cast<float4*>(p) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]);      // one STS.128
-}
-__device__ __forceinline__ Quad<double> quad_load(const Quad<double>* p) {
-    const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
-    Quad<double> q; q.v[0] = a.x; q.v[1] = a.y; q.v[2] = b.x; q.v[3] = b.y;
-    return q;
-}
-__device__ __forceinline__ void quad_store(Quad<double>* p, const Quad<double>& q) {
-    reinterpret_cast<double2*>(p)[0] = make_double2(q.v[0], q.v[1]);
-    reinterpret_cast<double2*>(p)[1] = make_double2(q.v[2], q.v[3]);
-}
-
 template <typename T>
 struct MapGradCache {
     Quad<T> z[kMaxPointsPerLane * 32];               // d/dz of the point's current cell corners (00, 10, 01, 11)

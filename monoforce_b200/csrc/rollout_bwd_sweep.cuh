@@ -46,28 +46,6 @@ __device__ __forceinline__ double pack_cell(int c, double) { return __longlong_a
 __device__ __forceinline__ int unpack_cell(float v) { return __float_as_int(v); }
 __device__ __forceinline__ int unpack_cell(double v) { return (int)__double_as_longlong(v); }
 
-template <typename T>
-struct SweepPoints {
-    Quad<T> pp[kMaxPointsPerLane * 32];     // (px, py, pz, side)   side: 0 not driven, -+half_Ly left / right track
-    T drv[kMaxPointsPerLane * 32];          // 1 if the point belongs to a driving part else 0
-};
-
-template <typename T>
-__device__ __forceinline__ void fill_sweep_points(SweepPoints<T>& tab, const RolloutArgs<T>& a, int slots) {
-    for (int p = threadIdx.x; p < slots; p += blockDim.x) {
-        Quad<T> q; q.v[0] = q.v[1] = q.v[2] = q.v[3] = (T)0;
-        T d = (T)0;
-        if (p < a.N) {
-            q.v[0] = a.pts[p * 3 + 0]; q.v[1] = a.pts[p * 3 + 1]; q.v[2] = a.pts[p * 3 + 2];
-            const int part = a.part[p];
-            d = part >= 0 ? (T)1 : (T)0;
-            q.v[3] = part < 0 ? (T)0 : ((part & 1) ? a.half_Ly : -a.half_Ly);     // dphysics.py:75-104
-        }
-        quad_store(&tab.pp[p], q);
-        tab.drv[p] = d;
-    }
-}
-
 // off-map samples use the reference's clamped flat indices; their gradients go straight to the caller's maps (rare)
 template <typename T>
 __device__ __noinline__ void scatter_off_map(T* __restrict__ gz, T* __restrict__ gm, T ggx, T ggy, int H, int W,

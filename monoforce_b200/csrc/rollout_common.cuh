@@ -346,7 +346,9 @@ struct PointEval {
 };
 
 // `cells` / `zmap` / `fmap` are already offset to this trajectory's map.
-template <typename T>
+// PATCH_OFF_MAP = false: branch-free fast path; an off-map point (o.cell == -1) is evaluated on cell 0's record and the
+// caller must redo the step with PATCH_OFF_MAP = true if any lane reports one (rare).
+template <typename T, bool PATCH_OFF_MAP = true>
 __device__ __forceinline__ void eval_point(PointEval<T>& o, const StepFrame<T>& f, T px, T py, T pz, T drv, T side,
                                            bool valid, const T* __restrict__ cells, const T* __restrict__ zmap,
                                            const T* __restrict__ fmap, int H, int W, T inv_res, T stiffness, T damping) {
@@ -354,6 +356,8 @@ __device__ __forceinline__ void eval_point(PointEval<T>& o, const StepFrame<T>& 
     o.r[0] = f.R[0] * px + f.R[1] * py + f.R[2] * pz;
     o.r[1] = f.R[3] * px + f.R[4] * py + f.R[5] * pz;
     o.r[2] = f.R[6] * px + f.R[7] * py + f.R[8] * pz;
+    // (written as v + (a - b): the fused form fma(w1, r2, fma(-w2, r1, v0)) saves 3 instructions per point but measured
+    // SLOWER in both kernels, +2 %: longer dependent chain on the same registers)
     o.V[0] = f.v[0] + (f.w[1] * o.r[2] - f.w[2] * o.r[1]);
     o.V[1] = f.v[1] + (f.w[2] * o.r[0] - f.w[0] * o.r[2]);
     o.V[2] = f.v[2] + (f.w[0] * o.r[1] - f.w[1] * o.r[0]);
@@ -369,7 +373,7 @@ __device__ __forceinline__ void eval_point(PointEval<T>& o, const StepFrame<T>& 
     const int cell = on_map ? ix * W + iy : 0;
     load_cell_record(cells + (long long)cell * kCellRec, o.rec);
     o.cell = on_map ? cell : -1;
-    if (!on_map) {
+    if (PATCH_OFF_MAP && !on_map) {
         // the record goes through a local buffer so that o.rec itself stays in registers
         T tmp[kCellRec + 2];
         sample_off_map(zmap, fmap, gx, gy, H, W, inv_res, tmp);
@@ -423,6 +427,52 @@ __device__ __forceinline__ void invert_inertia(const T* m6, T* inv9) {
     inv9[0] = A * r;            inv9[1] = B * r;            inv9[2] = Cc * r;
     inv9[3] = B * r;            inv9[4] = (a * f - c * c) * r; inv9[5] = (b * c - a * e) * r;
     inv9[6] = Cc * r;           inv9[7] = (b * c - a * e) * r; inv9[8] = (a * d - b * b) * r;
+}
+
+// 4 scalars moved as one (float) or two (double) 16-byte shared-memory accesses
+template <typename T> struct Quad;                       // 4 scalars moved as one or two 16-byte shared accesses
+template <> struct __align__(16) Quad<float> { float v[4]; };
+template <> struct __align__(16) Quad<double> { double v[4]; };
+
+__device__ __forceinline__ Quad<float> quad_load(const Quad<float>* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);       // one LDS.128
+    Quad<float> q; q.v[0] = t.x; q.v[1] = t.y; q.v[2] = t.z; q.v[3] = t.w;
+    return q;
+}
+__device__ __forceinline__ void quad_store(Quad<float>* p, const Quad<float>& q) {
+    *reinterpret_cast<float4*>(p) = make_float4(q.v[0], q.v[1], q.v[2], q.v[3]);      // one STS.128
+}
+__device__ __forceinline__ Quad<double> quad_load(const Quad<double>* p) {
+    const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+    Quad<double> q; q.v[0] = a.x; q.v[1] = a.y; q.v[2] = b.x; q.v[3] = b.y;
+    return q;
+}
+__device__ __forceinline__ void quad_store(Quad<double>* p, const Quad<double>& q) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(q.v[0], q.v[1]);
+    reinterpret_cast<double2*>(p)[1] = make_double2(q.v[2], q.v[3]);
+}
+
+// packed body-point table: one 16-byte load + one scalar load per point instead of five scalar loads
+template <typename T>
+struct SweepPoints {
+    Quad<T> pp[kMaxPointsPerLane * 32];     // (px, py, pz, side)   side: 0 not driven, -+half_Ly left / right track
+    T drv[kMaxPointsPerLane * 32];          // 1 if the point belongs to a driving part else 0
+};
+
+template <typename T>
+__device__ __forceinline__ void fill_sweep_points(SweepPoints<T>& tab, const RolloutArgs<T>& a, int slots) {
+    for (int p = threadIdx.x; p < slots; p += blockDim.x) {
+        Quad<T> q; q.v[0] = q.v[1] = q.v[2] = q.v[3] = (T)0;
+        T d = (T)0;
+        if (p < a.N) {
+            q.v[0] = a.pts[p * 3 + 0]; q.v[1] = a.pts[p * 3 + 1]; q.v[2] = a.pts[p * 3 + 2];
+            const int part = a.part[p];
+            d = part >= 0 ? (T)1 : (T)0;
+            q.v[3] = part < 0 ? (T)0 : ((part & 1) ? a.half_Ly : -a.half_Ly);     // dphysics.py:75-104
+        }
+        quad_store(&tab.pp[p], q);
+        tab.drv[p] = d;
+    }
 }
 
 // Body points staged once per block: slot = j*32 + lane == point index.  Padded slots (only in

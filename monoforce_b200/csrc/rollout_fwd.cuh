@@ -11,11 +11,15 @@
 //   warp reduction of 9 partial sums, then the semi-implicit Euler + Rodrigues update
 //   redundantly in every lane, record the post-update state.
 #pragma once
+#include <type_traits>
 #include "rollout_common.cuh"
 
 namespace mfb {
 
 constexpr int kFwdWarps = 4;   // trajectories per CTA
+#ifndef MFB_FWD_REDO
+#define MFB_FWD_REDO 1      // 1: branch-free phase 1 + whole-step redo when a point is off the map
+#endif
 #ifndef MFB_FWD_MINB
 #define MFB_FWD_MINB 4        // resident CTAs per SM the fp32 kernel is compiled for (128 registers)
 #endif
@@ -67,8 +71,10 @@ __device__ __forceinline__ void emit_rows(T* __restrict__ grow_s, T* __restrict_
 template <typename T, int PPL, int VARIANT, bool FORCES, bool COST, bool JOINTS = false>
 __global__ void __launch_bounds__(kFwdWarps * 32, (sizeof(T) == 4 && PPL <= 7) ? MFB_FWD_MINB : 1)
 rollout_fwd_kernel(const RolloutArgs<T> a) {
-    __shared__ PointTable<T> tab;
-    fill_point_table(tab, a, PPL * 32);
+    __shared__ PointTable<T> tab;          // scalar arrays: snap + moving-flipper variant
+    __shared__ SweepPoints<T> ptab;        // packed (px, py, pz, side) + driven flag: the step loop of the static variant
+    if (JOINTS) fill_point_table(tab, a, PPL * 32);
+    else fill_sweep_points(ptab, a, PPL * 32);
     __syncthreads();
 
     const int lane = lane_id();
@@ -99,9 +105,15 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
             const int slot = j * 32 + lane;
+            T px, py, pz;
+            if (JOINTS) {
+                px = tab.px[slot]; py = tab.py[slot]; pz = tab.pz[slot];
+            } else {
+                const Quad<T> pq = quad_load(&ptab.pp[slot]);
+                px = pq.v[0]; py = pq.v[1]; pz = pq.v[2];
+            }
             PointEval<T> e;
-            eval_point(e, f, tab.px[slot], tab.py[slot], tab.pz[slot], (T)0, (T)0, true, cells, zmap, fmap, H, W,
-                       a.inv_res, a.stiffness, a.damping);
+            eval_point(e, f, px, py, pz, (T)0, (T)0, true, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
             const T zv = e.rec[0] + e.fy * e.rec[1] + e.fx * e.dz_dfx;
             acc += (j == PPL - 1 && !last_valid) ? (T)0 : zv;
         }
@@ -112,6 +124,7 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
 
     // cost accumulators (Welford over steps of the per-step std over points)
     T cost_mean = (T)0, cost_m2 = (T)0;
+    const T inv_n = (T)1 / (T)a.N, inv_nm1 = (T)1 / (T)(a.N - 1);    // N == 1: 0 * inf = NaN, like torch.std
 
     const long long rowF = (long long)a.N * 3;
     T* __restrict__ Fs_b = FORCES ? a.Fs + (long long)b * a.nT * rowF : nullptr;
@@ -175,25 +188,49 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
             Mth<T>::sincos(ang, &js, &jc);
         }
 
-#pragma unroll
-        for (int j = 0; j < PPL; ++j) {
-            const int slot = j * 32 + lane;
-            T px = tab.px[slot], py = tab.py[slot], pz = tab.pz[slot];
+        // phase 1 over the lane's points.  First without the off-map patch (branch free: the loads of all points are in
+        // flight together); if any lane saw a point outside the map the step is redone with the patching version.
+        auto phase1 = [&](auto patch) -> bool {
+            constexpr bool kPatch = decltype(patch)::value;
+            bool off = false;
+            C = (T)0;
             if (JOINTS) {
-                articulate_point(px, py, pz, tab.part[slot], jc, js, a.joint_pos);
-                if ((j < PPL - 1) || last_valid) {
-                    mom[0] += py * py + pz * pz; mom[1] += px * px + pz * pz; mom[2] += px * px + py * py;
-                    mom[3] += px * py; mom[4] += px * pz; mom[5] += py * pz;
-                }
-            }
-            PointEval<T> e;
-            eval_point(e, f, px, py, pz, tab.driven[slot], tab.side[slot],
-                       (j < PPL - 1) || last_valid, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
-            C += e.cw;
-            sc[j] = e.sp * e.cw;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { slip[j][k] = e.sl[k]; nrm[j][k] = e.rec[4 + k]; arm[j][k] = e.r[k]; }
-        }
+                for (int k = 0; k < 6; ++k) mom[k] = (T)0;
+            }
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) {
+                const int slot = j * 32 + lane;
+                T px, py, pz, drv, side;
+                if (JOINTS) {
+                    px = tab.px[slot]; py = tab.py[slot]; pz = tab.pz[slot]; drv = tab.driven[slot]; side = tab.side[slot];
+                } else {
+                    const Quad<T> pq = quad_load(&ptab.pp[slot]);
+                    px = pq.v[0]; py = pq.v[1]; pz = pq.v[2]; side = pq.v[3]; drv = ptab.drv[slot];
+                }
+                if (JOINTS) {
+                    articulate_point(px, py, pz, tab.part[slot], jc, js, a.joint_pos);
+                    if ((j < PPL - 1) || last_valid) {
+                        mom[0] += py * py + pz * pz; mom[1] += px * px + pz * pz; mom[2] += px * px + py * py;
+                        mom[3] += px * py; mom[4] += px * pz; mom[5] += py * pz;
+                    }
+                }
+                PointEval<T> e;
+                eval_point<T, kPatch>(e, f, px, py, pz, drv, side,
+                                      (j < PPL - 1) || last_valid, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
+                off |= e.cell < 0;
+                C += e.cw;
+                sc[j] = e.sp * e.cw;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { slip[j][k] = e.sl[k]; nrm[j][k] = e.rec[4 + k]; arm[j][k] = e.r[k]; }
+            }
+            return off;
+        };
+#if MFB_FWD_REDO
+        if (__any_sync(kFull, phase1(std::false_type{}))) phase1(std::true_type{});
+#else
+        phase1(std::true_type{});
+#endif
 
         C = warp_sum(C);
         const T invC = Mth<T>::rcp(C);
@@ -206,6 +243,8 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
         T h = (T)0;
         if (VARIANT == kOdeintEuler) h = a.ts[t + 1] - a.ts[t];
 
+        // row pointers are re-derived from t every step: carrying them across the loop costs 5 registers and measured
+        // +0.19 ms (spills) at 128 registers / thread
         T* __restrict__ Fs_t = FORCES ? Fs_b + (long long)(VARIANT == kOdeintEuler ? t + 1 : t) * rowF : nullptr;
         T* __restrict__ Ff_t = FORCES ? Ff_b + (long long)(VARIANT == kOdeintEuler ? t + 1 : t) * rowF : nullptr;
         // phase of the row start inside a 16-byte line (both tensors share it: same shape, 16-byte aligned bases)
@@ -225,9 +264,9 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
             const T Ft0 = clampT(Nf * slip[j][0], a.mg), Ft1 = clampT(Nf * slip[j][1], a.mg), Ft2 = clampT(Nf * slip[j][2], a.mg);
             const T F0 = Fr0 + Ft0, F1 = Fr1 + Ft1, F2 = Fr2 + Ft2;
             sum[0] += F0; sum[1] += F1; sum[2] += F2;                                        // dphysics.py:265 (F_spring + F_friction)
-            sum[3] += arm[j][1] * F2 - arm[j][2] * F1;                                       // dphysics.py:255
-            sum[4] += arm[j][2] * F0 - arm[j][0] * F2;
-            sum[5] += arm[j][0] * F1 - arm[j][1] * F0;
+            sum[3] = fma(arm[j][1], F2, fma(-arm[j][2], F1, sum[3]));                        // dphysics.py:255
+            sum[4] = fma(arm[j][2], F0, fma(-arm[j][0], F2, sum[4]));
+            sum[5] = fma(arm[j][0], F1, fma(-arm[j][1], F0, sum[5]));
             if (COST) { nf_sum += Nf; nf_sq += Nf * Nf; }
             if (FORCES) {
                 if (j < PPL - 1 || last_valid) {
@@ -249,6 +288,7 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
             fence_async_smem();
             __syncwarp();
             emit_rows(Fs_t, Ff_t, img_s, img_f, phase, (int)rowF, lane);
+
         }
         {
             T red[8] = {sum[0], sum[1], sum[2], sum[3], sum[4], sum[5], nf_sum, nf_sq};
@@ -260,12 +300,12 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
 
         if (COST) {
             // unbiased std over the N points of |F_spring|, then Welford over steps
-            const T mean = nf_sum / (T)a.N;
-            T var = (nf_sq - nf_sum * mean) / (T)(a.N - 1);
+            const T mean = nf_sum * inv_n;
+            T var = (nf_sq - nf_sum * mean) * inv_nm1;
             var = Mth<T>::fmax_(var, (T)0);
             const T sd = Mth<T>::sqrt_rn(var);
             const T d = sd - cost_mean;
-            cost_mean += d / (T)(t + 1);
+            cost_mean += d * Mth<T>::inv((T)(t + 1));
             cost_m2 += d * (sd - cost_mean);
         }
 

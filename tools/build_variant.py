@@ -10,6 +10,7 @@ sys.path.insert(0, ROOT)
 from monoforce_b200 import build as B
 
 name, units, flags = sys.argv[1], sys.argv[2].split(","), sys.argv[3:]
+CSRC = os.environ.get("MFB_CSRC", B.CSRC)      # alternative source tree (e.g. a checkout of an older commit)
 B.build(verbose=False)
 out_dir = os.path.join(ROOT, "tools", "scratch", "variants")
 os.makedirs(out_dir, exist_ok=True)
@@ -18,7 +19,8 @@ for uname, src, defs in B._units():
     o = os.path.join(B.OBJ, uname + ".o")
     if uname in units:
         o = os.path.join(out_dir, f"{name}_{uname}.o")
-        cmd = [B._nvcc(), *B.ARCH, *B.COMMON, *defs, *flags, "-Xptxas", "-v", "-c", os.path.join(B.CSRC, src), "-o", o]
+        common = [c if c != B.CSRC else CSRC for c in B.COMMON]
+        cmd = [B._nvcc(), *B.ARCH, *common, *defs, *flags, "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.exit(r.stderr)
