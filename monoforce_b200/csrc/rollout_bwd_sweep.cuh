@@ -31,9 +31,15 @@ namespace mfb {
 #ifndef MFB_SWEEP_PARK
 #define MFB_SWEEP_PARK 1       // 1: the carried state adjoint waits in shared memory while the point loop runs (-18 registers)
 #endif
+#ifndef MFB_SWEEP_FRAME_SMEM
+#define MFB_SWEEP_FRAME_SMEM 2  // warp-uniform per-step operands are re-read from shared memory at every point instead of living in
+                                // registers.  1: v, w, controls, thrust direction, tq_bar, fs_bar, 1/C (-20 registers, +5 loads / point);
+                                // 2: also R, x.z and the grid offsets (-12 more, +3 loads).  Measured at config 3 (B200): 0 -> 8.25 ms
+                                // (168 regs, 12 warps/SM), 1 -> 7.9 ms and 2 -> 7.5 ms (128 regs, 16 warps/SM)
+#endif
 constexpr int kSweepWarps = MFB_SWEEP_WARPS;
 #ifndef MFB_SWEEP_MINB
-#define MFB_SWEEP_MINB 3
+#define MFB_SWEEP_MINB 4        // 4 CTAs x 4 warps = 16 warps / SM at 128 registers
 #endif
 #ifndef MFB_SWEEP_UNROLL
 #define MFB_SWEEP_UNROLL 1
@@ -62,6 +68,20 @@ __device__ __noinline__ void fixup_off_map(T* __restrict__ gz, T coef, T ggx, T 
     const T gx = (T)1 - fx, gy = (T)1 - fy;
     scatter_off_map<T>(gz, nullptr, ggx, ggy, H, W, coef * gx * gy, coef * gx * fy, coef * fx * gy, coef * fx * fy,
                        (T)0, (T)0, (T)0, (T)0);
+}
+
+// shared-memory quad load the compiler may not hoist out of the point loop
+__device__ __forceinline__ Quad<float> quad_load_pinned(const Quad<float>* p) {
+    Quad<float> q;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(q.v[0]), "=f"(q.v[1]), "=f"(q.v[2]), "=f"(q.v[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return q;
+}
+__device__ __forceinline__ Quad<double> quad_load_pinned(const Quad<double>* p) {
+    Quad<double> q;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.v[0]), "=d"(q.v[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(q.v[2]), "=d"(q.v[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return q;
 }
 
 template <typename T>
@@ -182,6 +202,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
     static_assert(!(VARIANT == kOdeintEuler && HAS_FGRAD), "odeint + force gradients: use the three-pass kernel");
     __shared__ SweepPoints<T> tab;
     __shared__ Quad<T> park_all[MFB_SWEEP_PARK ? kSweepWarps * 5 : 1];
+    __shared__ Quad<T> frame_all[MFB_SWEEP_FRAME_SMEM ? kSweepWarps * 8 : 1];
     const int ppl = (a.N + 31) >> 5;
     const int slots = ppl * 32;
     fill_sweep_points(tab, a, slots);
@@ -308,6 +329,21 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             q.v[0] = Rb[7]; q.v[1] = Rb[8]; q.v[2] = hd_norm; q.v[3] = (T)0; quad_store(pk + 4, q);
             __syncwarp();
         }
+        Quad<T>* const fr = frame_all + (MFB_SWEEP_FRAME_SMEM ? warp * 8 : 0);
+        if (MFB_SWEEP_FRAME_SMEM) {
+            Quad<T> q;
+            q.v[0] = f.v[0]; q.v[1] = f.v[1]; q.v[2] = f.v[2]; q.v[3] = f.w[0]; quad_store(fr + 0, q);
+            q.v[0] = f.w[1]; q.v[1] = f.w[2]; q.v[2] = f.uv; q.v[3] = f.uw; quad_store(fr + 1, q);
+            q.v[0] = f.hd[0]; q.v[1] = f.hd[1]; q.v[2] = f.hd[2]; q.v[3] = invC; quad_store(fr + 2, q);
+            q.v[0] = tq_b[0]; q.v[1] = tq_b[1]; q.v[2] = tq_b[2]; q.v[3] = fs_b0; quad_store(fr + 3, q);
+            q.v[0] = fs_b1; q.v[1] = fs_b2; q.v[2] = Cb_prev; q.v[3] = f.x[2]; quad_store(fr + 4, q);
+            if (MFB_SWEEP_FRAME_SMEM >= 2) {
+                q.v[0] = f.R[0]; q.v[1] = f.R[1]; q.v[2] = f.R[2]; q.v[3] = f.R[3]; quad_store(fr + 5, q);
+                q.v[0] = f.R[4]; q.v[1] = f.R[5]; q.v[2] = f.R[6]; q.v[3] = f.R[7]; quad_store(fr + 6, q);
+                q.v[0] = f.R[8]; q.v[1] = f.ox; q.v[2] = f.oy; q.v[3] = (T)0; quad_store(fr + 7, q);
+            }
+            __syncwarp();
+        }
         // acc: 0-2 x_bar, 3-5 v_bar, 6-8 w_bar, 9-17 R_bar, 18-20 hd_bar, 21-22 controls, 23 sum f_bar f (-> C_bar)
         // kap: 0-2 x_bar per unit C_bar, 3-11 R_bar per unit C_bar
         T acc[24], kap[12];
@@ -322,14 +358,40 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             const bool ok = slot < a.N;
             const Quad<T> pq = quad_load(&tab.pp[slot]);
             const T px = pq.v[0], py = pq.v[1], pz = pq.v[2], side = pq.v[3], drv = tab.drv[slot];
+            // warp-uniform operands of this step: registers, or re-read from shared memory (MFB_SWEEP_FRAME_SMEM)
+            StepFrame<T> fl = f;
+            T L_invC = invC, L_Cb_prev = Cb_prev, L_tq[3] = {tq_b[0], tq_b[1], tq_b[2]}, L_fs[3] = {fs_b0, fs_b1, fs_b2};
+            T L_w[3] = {s.w[0], s.w[1], s.w[2]};
+            if (MFB_SWEEP_FRAME_SMEM) {
+                const Quad<T> q0 = quad_load_pinned(fr + 0), q1 = quad_load_pinned(fr + 1), q2 = quad_load_pinned(fr + 2);
+                fl.v[0] = q0.v[0]; fl.v[1] = q0.v[1]; fl.v[2] = q0.v[2];
+                fl.w[0] = q0.v[3]; fl.w[1] = q1.v[0]; fl.w[2] = q1.v[1];
+                fl.uv = q1.v[2]; fl.uw = q1.v[3];
+                fl.hd[0] = q2.v[0]; fl.hd[1] = q2.v[1]; fl.hd[2] = q2.v[2];
+                L_invC = q2.v[3];
+                L_w[0] = fl.w[0]; L_w[1] = fl.w[1]; L_w[2] = fl.w[2];
+                if (MFB_SWEEP_FRAME_SMEM >= 2) {
+                    const Quad<T> q5 = quad_load_pinned(fr + 5), q6 = quad_load_pinned(fr + 6), q7 = quad_load_pinned(fr + 7);
+                    fl.R[0] = q5.v[0]; fl.R[1] = q5.v[1]; fl.R[2] = q5.v[2]; fl.R[3] = q5.v[3];
+                    fl.R[4] = q6.v[0]; fl.R[5] = q6.v[1]; fl.R[6] = q6.v[2]; fl.R[7] = q6.v[3];
+                    fl.R[8] = q7.v[0]; fl.ox = q7.v[1]; fl.oy = q7.v[2];
+                }
+            }
             PointEval<T> e;
-            eval_point(e, f, px, py, pz, drv, side, ok, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
+            eval_point(e, fl, px, py, pz, drv, side, ok, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
             const T n0 = e.rec[4], n1 = e.rec[5], n2 = e.rec[6];
             const T fx = e.fx, fy = e.fy;
             const T r0 = e.r[0], r1 = e.r[1], r2 = e.r[2];
+            if (MFB_SWEEP_FRAME_SMEM) {
+                const Quad<T> q3 = quad_load_pinned(fr + 3), q4 = quad_load_pinned(fr + 4);
+                L_tq[0] = q3.v[0]; L_tq[1] = q3.v[1]; L_tq[2] = q3.v[2];
+                L_fs[0] = q3.v[3]; L_fs[1] = q4.v[0]; L_fs[2] = q4.v[1];
+                L_Cb_prev = q4.v[2];
+                if (MFB_SWEEP_FRAME_SMEM >= 2) fl.x[2] = q4.v[3];
+            }
 
             // ---- phase 2 forward (dphysics.py:228-251) ----
-            const T fo = e.sp * e.cw * invC;
+            const T fo = e.sp * e.cw * L_invC;
             const T G0 = fo * n0, G1 = fo * n1, G2 = fo * n2;
             const T Fr0 = clampT(G0, a.mg), Fr1 = clampT(G1, a.mg), Fr2 = clampT(G2, a.mg);
             const T Nf2 = Fr0 * Fr0 + Fr1 * Fr1 + Fr2 * Fr2;
@@ -341,9 +403,9 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
 
             // ---- phase 2 reversed ----
             // torque = sum r x F :  F_bar += tq_bar x r ;  r_bar += F x tq_bar
-            T Frb0 = fs_b0 + (tq_b[1] * r2 - tq_b[2] * r1);
-            T Frb1 = fs_b1 + (tq_b[2] * r0 - tq_b[0] * r2);
-            T Frb2 = fs_b2 + (tq_b[0] * r1 - tq_b[1] * r0);
+            T Frb0 = L_fs[0] + (L_tq[1] * r2 - L_tq[2] * r1);
+            T Frb1 = L_fs[1] + (L_tq[2] * r0 - L_tq[0] * r2);
+            T Frb2 = L_fs[2] + (L_tq[0] * r1 - L_tq[1] * r0);
             T Ftb0 = Frb0, Ftb1 = Frb1, Ftb2 = Frb2;
             if (HAS_FGRAD) {
                 const long long o = ((long long)b * a.nT + rec) * rowF + (long long)slot * 3;
@@ -352,9 +414,9 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                     if (g.g_Ff) { Ftb0 += g.g_Ff[o]; Ftb1 += g.g_Ff[o + 1]; Ftb2 += g.g_Ff[o + 2]; }
                 }
             }
-            const T ab0 = F1 * tq_b[2] - F2 * tq_b[1];
-            const T ab1 = F2 * tq_b[0] - F0 * tq_b[2];
-            const T ab2 = F0 * tq_b[1] - F1 * tq_b[0];
+            const T ab0 = F1 * L_tq[2] - F2 * L_tq[1];
+            const T ab1 = F2 * L_tq[0] - F0 * L_tq[2];
+            const T ab2 = F0 * L_tq[1] - F1 * L_tq[0];
             // F_friction = clamp(Nf * slip)
             const T Hb0 = gate(Ftb0, Hh0, a.mg), Hb1 = gate(Ftb1, Hh1, a.mg), Hb2 = gate(Ftb2, Hh2, a.mg);
             const T Nf_b = Hb0 * e.sl[0] + Hb1 * e.sl[1] + Hb2 * e.sl[2];
@@ -371,7 +433,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
 
             // ---- phase 1 reversed (own terms; the C_bar share goes through the kappa channel) ----
             T nb0 = fo * Gb0, nb1 = fo * Gb1, nb2 = fo * Gb2;
-            const T sc_b = f_b * invC;
+            const T sc_b = f_b * L_invC;
             const T sp_b = sc_b * e.cw;
             const T cw_b = sc_b * e.sp;
             // slip = d - dn n ; dn = d . n
@@ -381,7 +443,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             // d = mu e ; e = tau hd - V
             const T mu_b = db0 * e.e[0] + db1 * e.e[1] + db2 * e.e[2];
             const T eb0 = e.mu * db0, eb1 = e.mu * db1, eb2 = e.mu * db2;
-            const T tau_b = eb0 * f.hd[0] + eb1 * f.hd[1] + eb2 * f.hd[2];
+            const T tau_b = eb0 * fl.hd[0] + eb1 * fl.hd[1] + eb2 * fl.hd[2];
             acc[18] += e.tau * eb0; acc[19] += e.tau * eb1; acc[20] += e.tau * eb2;
             acc[21] += drv * tau_b; acc[22] += side * tau_b;
             T Vb0 = -eb0, Vb1 = -eb1, Vb2 = -eb2;
@@ -415,8 +477,8 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                 {   // park this visit's (kappa, fx, fy, cell); off-map points keep their raw grid coordinates instead
                     Quad<T> np;
                     np.v[0] = kappa;
-                    np.v[1] = on_map ? fx : r0 * a.inv_res + f.ox;
-                    np.v[2] = on_map ? fy : r1 * a.inv_res + f.oy;
+                    np.v[1] = on_map ? fx : r0 * a.inv_res + fl.ox;
+                    np.v[2] = on_map ? fy : r1 * a.inv_res + fl.oy;
                     np.v[3] = pack_cell(e.cell, (T)0);
                     quad_store(rec + 2, np);
                 }
@@ -424,7 +486,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                 const bool same = cur == e.cell;
                 Quad<T> qz = quad_load(rec), qm = quad_load(rec + 1);
                 // (1) the previous visit's kappa-channel share, now that its C_bar is known
-                const T coef = -Cb_prev * pend.v[0];
+                const T coef = -L_Cb_prev * pend.v[0];
                 if (cur >= 0) {
                     const T pfx = pend.v[1], pfy = pend.v[2];
                     const T c0 = coef - coef * pfx, c1 = coef * pfx;
@@ -443,7 +505,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                     qm.v[2] = keep * qm.v[2] + mu_b * w01; qm.v[3] = keep * qm.v[3] + mu_b * w11;
                     quad_store(rec, qz); quad_store(rec + 1, qm);
                 } else {
-                    scatter_off_map(gz_dir, gm_dir, r0 * a.inv_res + f.ox, r1 * a.inv_res + f.oy, H, W, cgz0, cgz1, cgz2, cgz3,
+                    scatter_off_map(gz_dir, gm_dir, r0 * a.inv_res + fl.ox, r1 * a.inv_res + fl.oy, H, W, cgz0, cgz1, cgz2, cgz3,
                                     mu_b * w00, mu_b * w10, mu_b * w01, mu_b * w11);
                 }
             }
@@ -451,9 +513,9 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             // grid coordinate -> world point ; V = v + w x r ; P = r + x ; r = R p
             const T ires = a.inv_res;
             const T Pb0 = fx_b * ires, Pb1 = fy_b * ires, Pb2 = dh_b;
-            T rb0 = ab0 + Pb0 + (Vb1 * s.w[2] - Vb2 * s.w[1]);
-            T rb1 = ab1 + Pb1 + (Vb2 * s.w[0] - Vb0 * s.w[2]);
-            T rb2 = ab2 + Pb2 + (Vb0 * s.w[1] - Vb1 * s.w[0]);
+            T rb0 = ab0 + Pb0 + (Vb1 * L_w[2] - Vb2 * L_w[1]);
+            T rb1 = ab1 + Pb1 + (Vb2 * L_w[0] - Vb0 * L_w[2]);
+            T rb2 = ab2 + Pb2 + (Vb0 * L_w[1] - Vb1 * L_w[0]);
             if (!ok) { rb0 = rb1 = rb2 = (T)0; Vb0 = Vb1 = Vb2 = (T)0; }
             const T okf = ok ? (T)1 : (T)0;
             acc[0] += okf * Pb0; acc[1] += okf * Pb1; acc[2] += okf * Pb2;
@@ -474,6 +536,12 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             }
         }
 
+        if (MFB_SWEEP_FRAME_SMEM) {
+            // bring the operands the epilogue of the step needs back from shared memory (they did not occupy registers meanwhile)
+            const Quad<T> q0 = quad_load_pinned(fr + 0), q1 = quad_load_pinned(fr + 1), q2 = quad_load_pinned(fr + 2);
+            s.w[0] = q0.v[3]; s.w[1] = q1.v[0]; s.w[2] = q1.v[1];
+            f.hd[0] = q2.v[0]; f.hd[1] = q2.v[1]; f.hd[2] = q2.v[2];
+        }
         T hd_nrm = hd_norm;
         if (MFB_SWEEP_PARK) {
             const Quad<T>* pk = park_all + warp * 5;
@@ -486,7 +554,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             __syncwarp();
         }
         // C_bar first (one butterfly), so that every lane can close its kappa channel before the big reduction
-        const T C_b = -warp_sum(acc[23]) * invC;
+        const T C_b = -warp_sum(acc[23]) * (MFB_SWEEP_FRAME_SMEM ? quad_load_pinned(fr + 2).v[3] : invC);
         Cb_prev = C_b;
 #pragma unroll
         for (int i = 0; i < 3; ++i) acc[i] += C_b * kap[i];
