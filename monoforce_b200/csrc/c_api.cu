@@ -65,7 +65,7 @@ static RolloutArgs<T> make_args(const mfb_rollout_desc& d, const mfb_rollout_buf
     a.joint_angles = (const T*)io.joint_angles;
     for (int i = 0; i < 12; ++i) a.joint_pos[i] = (T)d.joint_positions[i];
     a.cells = (const T*)io.workspace;
-    a.cell_stride = d.map_stride == 0 ? 0 : (long long)d.H * d.W * kCellRec;
+    a.cell_stride = d.map_stride == 0 ? 0 : (long long)d.H * d.W * kCellStride;
     a.Xs = (T*)io.Xs; a.Xds = (T*)io.Xds; a.Rs = (T*)io.Rs; a.Oms = (T*)io.Omegas;
     a.Fs = (T*)io.F_springs; a.Ff = (T*)io.F_frictions; a.x0z = (T*)io.x0z; a.cost = (T*)io.cost;
     a.Csum = (T*)io.contact_sum;
@@ -87,7 +87,7 @@ static const char* check_io_forward(const mfb_rollout_desc& d, const mfb_rollout
 // workspace layout: [cell table: n_maps*H*W*12 scalars][map-gradient scratch: n_maps*H*W*8 scalars]
 static long long table_elems(const mfb_rollout_desc& d) {
     const long long n_maps = d.map_stride == 0 ? 1 : d.B;
-    return n_maps * d.H * d.W * kCellRec;
+    return n_maps * d.H * d.W * kCellStride;
 }
 constexpr int kGradScratchPerCell = 8;   // per-cell corner records of the single-sweep adjoint (the three-pass kernel uses 2)
 static long long workspace_bytes(const mfb_rollout_desc& d, int dtype) {

@@ -37,7 +37,12 @@ namespace mfb {
                                 // 2: also R, x.z and the grid offsets (-12 more, +3 loads).  Measured at config 3 (B200): 0 -> 8.25 ms
                                 // (168 regs, 12 warps/SM), 1 -> 7.9 ms and 2 -> 7.5 ms (128 regs, 16 warps/SM)
 #endif
+#ifndef MFB_SWEEP_PREFETCH
+#define MFB_SWEEP_PREFETCH 0    // 1: prefetch.global.L1 of the next point's cell record (from the cell of its previous visit); measured
+                                // slower (7.86 vs 7.60 ms): the extra shared-memory read + address math cost more than the L2 latency hidden
+#endif
 constexpr int kSweepWarps = MFB_SWEEP_WARPS;
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 #ifndef MFB_SWEEP_MINB
 #define MFB_SWEEP_MINB 4        // 4 CTAs x 4 warps = 16 warps / SM at 128 registers
 #endif
@@ -68,20 +73,6 @@ __device__ __noinline__ void fixup_off_map(T* __restrict__ gz, T coef, T ggx, T 
     const T gx = (T)1 - fx, gy = (T)1 - fy;
     scatter_off_map<T>(gz, nullptr, ggx, ggy, H, W, coef * gx * gy, coef * gx * fy, coef * fx * gy, coef * fx * fy,
                        (T)0, (T)0, (T)0, (T)0);
-}
-
-// shared-memory quad load the compiler may not hoist out of the point loop
-__device__ __forceinline__ Quad<float> quad_load_pinned(const Quad<float>* p) {
-    Quad<float> q;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(q.v[0]), "=f"(q.v[1]), "=f"(q.v[2]), "=f"(q.v[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-    return q;
-}
-__device__ __forceinline__ Quad<double> quad_load_pinned(const Quad<double>* p) {
-    Quad<double> q;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.v[0]), "=d"(q.v[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(q.v[2]), "=d"(q.v[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-    return q;
 }
 
 template <typename T>
@@ -356,6 +347,13 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
         for (int j = 0; j < ppl; ++j) {
             const int slot = j * 32 + lane;
             const bool ok = slot < a.N;
+            if (MFB_SWEEP_PREFETCH && gcell && j + 1 < ppl) {
+                // the NEXT point's cell record: with 16 warps per SM the table does not stay in L1 between two visits, but
+                // a point rarely leaves its cell within one step, so the cell it was in at its previous visit (parked in
+                // shared memory) tells where to prefetch
+                const int pc = unpack_cell(cache[3 * (slot + 32) + 2].v[3]);
+                if (pc >= 0) prefetch_l1(cells + (long long)pc * kCellStride);
+            }
             const Quad<T> pq = quad_load(&tab.pp[slot]);
             const T px = pq.v[0], py = pq.v[1], pz = pq.v[2], side = pq.v[3], drv = tab.drv[slot];
             // warp-uniform operands of this step: registers, or re-read from shared memory (MFB_SWEEP_FRAME_SMEM)

@@ -158,6 +158,8 @@ __device__ __forceinline__ int lane_id() {
 // 16-byte loads from one 48-byte record instead of eight scattered 4-byte gathers.
 // The neighbour indices use the reference's flat clamp (no per-axis clamp, :432-435).
 constexpr int kCellRec = 12;     // scalars per cell record: c0 cy cx cxy | n0 n1 n2 pad | m0 my mx mxy
+constexpr int kCellStride = 12;  // records are packed: padding them to 16 scalars (64 B, never straddling a 128-byte line) measured
+                                 // +11 % on the forward kernel (3 MB -> 4 MB table, fewer neighbouring cells per L1 line)
 
 struct Corners {
     int k00, k10, k01, k11;      // flat indices: centre, x+1 ("front"), y+1 ("left"), both
@@ -209,7 +211,7 @@ __global__ void build_cell_table_kernel(const T* __restrict__ z, const T* __rest
         const Corners c = flat_corners(ix, iy, H, W);
         T rec[kCellRec];
         make_cell_record(z + m * map_stride, mu + m * map_stride, c, inv_res, rec);
-        T* out = cells + i * kCellRec;
+        T* out = cells + i * kCellStride;
 #pragma unroll
         for (int j = 0; j < kCellRec; ++j) out[j] = rec[j];
     }
@@ -371,7 +373,7 @@ __device__ __forceinline__ void eval_point(PointEval<T>& o, const StepFrame<T>& 
     // the record load is unconditional (cell 0 stands in for off-map points) so that the loads of all
     // the lane's points can be in flight together; off-map points are patched afterwards (rare)
     const int cell = on_map ? ix * W + iy : 0;
-    load_cell_record(cells + (long long)cell * kCellRec, o.rec);
+    load_cell_record(cells + (long long)cell * kCellStride, o.rec);
     o.cell = on_map ? cell : -1;
     if (PATCH_OFF_MAP && !on_map) {
         // the record goes through a local buffer so that o.rec itself stays in registers
@@ -450,6 +452,20 @@ __device__ __forceinline__ Quad<double> quad_load(const Quad<double>* p) {
 __device__ __forceinline__ void quad_store(Quad<double>* p, const Quad<double>& q) {
     reinterpret_cast<double2*>(p)[0] = make_double2(q.v[0], q.v[1]);
     reinterpret_cast<double2*>(p)[1] = make_double2(q.v[2], q.v[3]);
+}
+
+// shared-memory quad load the compiler may not hoist out of the point loop
+__device__ __forceinline__ Quad<float> quad_load_pinned(const Quad<float>* p) {
+    Quad<float> q;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(q.v[0]), "=f"(q.v[1]), "=f"(q.v[2]), "=f"(q.v[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return q;
+}
+__device__ __forceinline__ Quad<double> quad_load_pinned(const Quad<double>* p) {
+    Quad<double> q;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q.v[0]), "=d"(q.v[1]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(q.v[2]), "=d"(q.v[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return q;
 }
 
 // packed body-point table: one 16-byte load + one scalar load per point instead of five scalar loads
