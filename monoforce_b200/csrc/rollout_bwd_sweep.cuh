@@ -200,7 +200,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
     __syncthreads();
 
     const int lane = lane_id();
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_id_pinned();     // opaque: or the compiler re-derives it from S2R %tid all over the point loop
     const int b = blockIdx.x * kSweepWarps + warp;
     if (b >= a.B) return;
 

@@ -145,6 +145,12 @@ __device__ __forceinline__ int lane_id() {
     return l;
 }
 
+__device__ __forceinline__ int warp_id_pinned() {
+    int t;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    return t >> 5;
+}
+
 // ------------------------------------------------------------------------------------------
 // grid sampling (dphysics.py:385-455) through a packed per-cell table
 // ------------------------------------------------------------------------------------------
