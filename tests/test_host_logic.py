@@ -20,7 +20,29 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.mfb_abi_version() == 1
+    assert lib.mfb_abi_version() == int(re.search(r"#define MFB_ABI_VERSION (\d+)", header).group(1)) == 2
+
+
+def test_ctypes_structs_mirror_the_header_field_for_field():
+    """The ctypes Structures in _lib.py must list the header's struct members in the same order (the boundary is plain C)."""
+    from monoforce_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "monoforce_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+
+    def members(name):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), header, re.S).group(1)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                out.append(re.search(r"([A-Za-z_][A-Za-z0-9_]*)\s*(\[\d+\])?\s*$", part.strip()).group(1))
+        return out
+
+    assert members("mfb_rollout_desc") == [f[0] for f in _lib.RolloutDesc._fields_]
+    assert members("mfb_rollout_buffers") == [f[0] for f in _lib.RolloutBuffers._fields_]
+    assert members("mfb_rollout_grads") == [f[0] for f in _lib.RolloutGrads._fields_]
     assert _lib.kernel_launches() >= 0
 
 
@@ -28,7 +50,7 @@ def test_struct_layouts_match_header_sizes():
     from monoforce_b200 import _lib
     # 8 int32 + int64 + 9 doubles + 9 doubles
     assert C.sizeof(_lib.RolloutDesc) == 8 * 4 + 8 + 9 * 8 + 9 * 8 + 12 * 8
-    assert C.sizeof(_lib.RolloutBuffers) == 19 * 8 + 8 + 8
+    assert C.sizeof(_lib.RolloutBuffers) == 20 * 8 + 8 + 8      # 11 inputs + 9 outputs (incl. the contact_sum tape) + workspace
     assert C.sizeof(_lib.RolloutGrads) == 15 * 8
 
 
@@ -37,7 +59,7 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     lib = _lib.load()
     d = _lib.RolloutDesc(B=4, T=10, N=223, H=64, W=64, n_tracks=4, variant=0, map_stride=0, mass=60., gravity=9.81,
                          stiffness=5e4, damping=3464., grid_res=0.1, d_max=6.4, dt=0.01, omega_max=2., robot_Ly=.5)
-    assert lib.mfb_rollout_workspace_bytes(C.byref(d), _lib.MFB_F32) == 64 * 64 * 14 * 4
+    assert lib.mfb_rollout_workspace_bytes(C.byref(d), _lib.MFB_F32) == 64 * 64 * (12 + 8) * 4   # sampling record + corner-gradient record per cell
     io = _lib.RolloutBuffers()
     assert lib.mfb_rollout_forward(C.byref(d), C.byref(io), _lib.MFB_F32, None) == -1
     assert b"NULL" in lib.mfb_last_error()

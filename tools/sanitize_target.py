@@ -16,8 +16,10 @@ for robot, variant in (("marv", False), ("tradr", True)):
     c = (torch.rand(B, T, 2, generator=g) * 2 - 1).to(dev).requires_grad_(True)
     x0 = torch.zeros(B, 3, device=dev); x0[0, 0] = 6.5; x0[1, 1] = -6.6     # two robots partly off the map
     st = (x0, torch.zeros(B, 3, device=dev), torch.eye(3, device=dev).repeat(B, 1, 1), torch.zeros(B, 3, device=dev))
-    (Xs, Xd, Rs, Om), (Fs, Ff) = sim(z.unsqueeze(0), c, state=st, friction=fr.unsqueeze(0))
-    (Xs.sum() + Rs.sum() + 1e-3 * Fs.sum() + 1e-3 * Ff.sum()).backward()
+    for tape in (True, False):          # single-sweep adjoint (contact_sum tape) and three-pass adjoint
+        sim.adjoint_tape = tape
+        (Xs, Xd, Rs, Om), (Fs, Ff) = sim(z.unsqueeze(0), c, state=st, friction=fr.unsqueeze(0))
+        (Xs.sum() + Rs.sum() + 1e-3 * Fs.sum() + 1e-3 * Ff.sum()).backward()
     if robot == "marv":
         with torch.no_grad():
             sim(z.detach().unsqueeze(0), c.detach(), joint_angles=torch.full((B, T, 4), 0.3, device=dev))
