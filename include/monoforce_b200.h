@@ -159,6 +159,20 @@ int mfb_lift_splat_backward(const void* logits, const void* vox, const void* g_b
 int mfb_conv_bn_act_bf16(const void* x, const void* wgt, const void* scale, const void* shift, void* y,
                          int N, int H, int W, int Cin, int Cout, int KS, int act, void* stream);
 
+/* ---- training objective fused with its gradient -------------------------------------------
+ * Replaces physics_loss (monoforce/src/monoforce/losses.py:102-138) and its autograd backward:
+ *   j(b,k) = argmin_j |pred_ts[b,j] - gt_ts[b,k]|,  w = 1 / (1 + gamma gt_ts[b,k]),
+ *   loss   = mean_{b,k,c} (X_pred[b,j,c] w - X_gt[b,k,c] w)^2          -> loss (1 scalar)
+ *   g_X_pred[b,j,c] (+)= d loss / d X_pred                             (NULL: not wanted)
+ * X_pred (B,T1,3), X_gt (B,T2,3); pred_ts / gt_ts rows are `*_ts_stride` scalars apart (0: one row shared by the
+ * batch).  same_time_grid != 0 promises pred_ts == gt_ts element for element (then j = k, pred_ts may be NULL and
+ * g_X_pred is written, not accumulated); otherwise g_X_pred must be zero-initialised.  scratch: device buffer of
+ * MFB_PHYSICS_LOSS_MAX_BLOCKS doubles.  The rotation term of the reference is not used by any shipped caller. */
+#define MFB_PHYSICS_LOSS_MAX_BLOCKS 4096
+int mfb_physics_loss(const void* X_pred, const void* X_gt, const void* pred_ts, const void* gt_ts,
+                     int64_t pred_ts_stride, int64_t gt_ts_stride, int B, int T1, int T2, double gamma,
+                     int same_time_grid, void* loss, void* g_X_pred, void* scratch, int dtype, void* stream);
+
 /* ---- bookkeeping ------------------------------------------------------------------------- */
 const char* mfb_last_error(void);
 int mfb_abi_version(void);

@@ -14,10 +14,11 @@ LIB_PATH = os.environ.get("MFB_LIB_PATH") or os.path.join(_PKG, "libmonoforce_b2
 
 MFB_F32, MFB_F64 = 0, 1
 MFB_STEP_LOOP, MFB_ODEINT_EULER = 0, 1
+MFB_PHYSICS_LOSS_MAX_BLOCKS = 4096
 
 EXPORTED_SYMBOLS = (
     "mfb_rollout_workspace_bytes", "mfb_rollout_forward", "mfb_rollout_backward", "mfb_rollout_forward_host",
-    "mfb_lift_splat_forward", "mfb_lift_splat_backward", "mfb_conv_bn_act_bf16",
+    "mfb_lift_splat_forward", "mfb_lift_splat_backward", "mfb_conv_bn_act_bf16", "mfb_physics_loss",
     "mfb_last_error", "mfb_abi_version", "mfb_kernel_launches", "mfb_release_scratch",
 )
 
@@ -79,6 +80,9 @@ def load() -> C.CDLL:
     lib.mfb_lift_splat_backward.restype = C.c_int
     lib.mfb_conv_bn_act_bf16.argtypes = [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_void_p]
     lib.mfb_conv_bn_act_bf16.restype = C.c_int
+    lib.mfb_physics_loss.argtypes = ([C.c_void_p] * 4 + [C.c_int64] * 2 + [C.c_int] * 3 + [C.c_double, C.c_int] +
+                                     [C.c_void_p] * 3 + [C.c_int, C.c_void_p])
+    lib.mfb_physics_loss.restype = C.c_int
     lib.mfb_last_error.restype = C.c_char_p
     lib.mfb_abi_version.restype = C.c_int
     lib.mfb_kernel_launches.restype = C.c_longlong

@@ -552,3 +552,41 @@ def test_fp32_ragged_sizes_forces_bit_pattern():
             _, f32 = sim(z.float().to(DEV).unsqueeze(0), controls.float().to(DEV), state=tuple(s.float().to(DEV) for s in st))
         assert torch.isfinite(f32[0]).all() and torch.isfinite(f32[1]).all()
         assert rel_err(f32[0], f64[0]) < 1e-3 and rel_err(f32[1], f64[1], 1e-6) < 5e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("case", ["same_grid", "shared_rows", "per_trajectory_rows"])
+def test_fused_physics_loss_matches_reference_definition(case, dtype):
+    """K6 (losses.py:102-138 fused with its gradient) vs the oracle's restatement of the reference and torch autograd:
+    identical time grids (identity gather), one (1,T) row of stamps shared by the batch, and per-trajectory stamps with
+    T2 != T1 (nearest-stamp search, several ground-truth stamps hitting the same predicted index)."""
+    from monoforce_b200.losses import physics_loss
+    from oracle.dphysics_oracle import physics_loss as ref_loss
+    g = torch.Generator().manual_seed(3)
+    B, T1 = 37, 90
+    Xp = torch.randn(B, T1, 3, generator=g, dtype=dtype)
+    if case == "same_grid":
+        T2 = T1
+        pred_ts = gt_ts = (torch.arange(T1, dtype=dtype) * 0.01)[None]
+    elif case == "shared_rows":
+        T2 = 23
+        pred_ts = (torch.arange(T1, dtype=dtype) * 0.01)[None]
+        gt_ts = torch.sort(torch.rand(1, T2, generator=g, dtype=dtype) * 0.9)[0]
+    else:
+        T2 = 41
+        pred_ts = torch.cumsum(torch.rand(B, T1, generator=g, dtype=dtype) * 0.02 + 1e-3, dim=1)
+        gt_ts = torch.sort(torch.rand(B, T2, generator=g, dtype=dtype) * 1.2)[0]
+    Xg = torch.randn(B, T2, 3, generator=g, dtype=dtype)
+    Xr = Xp.clone().requires_grad_(True)
+    lr = ref_loss((Xr,), (Xg,), pred_ts, gt_ts, 0.7)
+    (3.0 * lr).backward()
+    Xk = Xp.clone().to(DEV).requires_grad_(True)
+    pk = pred_ts.to(DEV)
+    gk = pk if case == "same_grid" else gt_ts.to(DEV)
+    n0 = __import__("monoforce_b200")._lib.kernel_launches()
+    lk = physics_loss((Xk,), (Xg.to(DEV),), pk, gk, 0.7)
+    assert __import__("monoforce_b200")._lib.kernel_launches() - n0 == 2       # the fused kernel + its one-block finish
+    (3.0 * lk).backward()
+    tol = 1e-5 if dtype == torch.float32 else 1e-12
+    assert abs(lk.item() - lr.item()) <= tol * abs(lr.item())
+    assert rel_err(Xk.grad, Xr.grad) < (1e-5 if dtype == torch.float32 else 1e-12)
