@@ -272,6 +272,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         fwd_only_ms = t.item()
 
+    # ---- training step that never materialises the two force tensors (reported separately, never as an HBM fraction) ----
+    sim.return_forces = False
+    for _ in range(2):
+        step()
+    barrier()
+    n_a, n_b = ev(), ev()
+    n_a.record()
+    for _ in range(args.steps):
+        step()
+    n_b.record()
+    barrier()
+    sim.return_forces = True
+    noforce_ms = n_a.elapsed_time(n_b) / args.steps
+    if world > 1:
+        t = torch.tensor([noforce_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        noforce_ms = t.item()
+
     # ---- end to end through the public API with HOST inputs / outputs ----
     h_controls, h_z, h_fr = d["controls"], d["z0"], d["fr0"]
     h_gz = torch.empty_like(h_z).pin_memory()
@@ -380,6 +398,9 @@ def main():
                            "backward_call (cell table + rollout_bwd + grad scatter)": bwd_ms},
             "forward_only": {"value": world * B * T_STEPS / (fwd_only_ms * 1e-3), "unit": UNIT, "ms_per_step": fwd_only_ms,
                              "workload": "BASELINE config 2 (forward only, all outputs materialised)"},
+            "states_only_training": {"value": world * B * T_STEPS / (noforce_ms * 1e-3), "unit": UNIT, "ms_per_step": noforce_ms,
+                                     "workload": "same step with DPhysics.return_forces=False (states + fused cost only; issue-bound, "
+                                                 "not an HBM number)"},
             "e2e": {"value": world * B * T_STEPS / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "path": "DPhysics.forward with pinned host controls/maps -> loss, map gradients and costs read back"},
