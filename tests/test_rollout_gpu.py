@@ -590,3 +590,42 @@ def test_fused_physics_loss_matches_reference_definition(case, dtype):
     tol = 1e-5 if dtype == torch.float32 else 1e-12
     assert abs(lk.item() - lr.item()) <= tol * abs(lr.item())
     assert rel_err(Xk.grad, Xr.grad) < (1e-5 if dtype == torch.float32 else 1e-12)
+
+
+def test_full_size_adjoint_properties_cfg3():
+    """BASELINE config 3 size (4096 x 400, 256^2 shared map, fp32): size-independent properties of the adjoint.
+    (i) the single-sweep kernel (contact_sum tape + kappa channel) and the three-pass kernel differentiate the same
+    recorded rollout, so their gradients agree to summation-order rounding; (ii) duplicated controls give duplicated
+    control gradients; (iii) the adjoint is linear in the seed: doubling the objective doubles every gradient;
+    (iv) the map gradients of the shared map are finite and non-trivial, the friction gradient only touches cells the
+    robots visited."""
+    from monoforce_b200.losses import physics_loss
+    T, B = 400, 4096
+    sim, cfg = _module("marv", 0.05, T)
+    sim.return_forces = False                      # the training path: the objective reads states only
+    gen = torch.Generator().manual_seed(1)
+    half = torch.stack([torch.rand(B // 2, generator=gen) * 0.5 + 0.5, torch.rand(B // 2, generator=gen) * 4 - 2], -1)
+    controls = torch.cat([half, half], 0).unsqueeze(1).repeat(1, T, 1).to(DEV)
+    ts = (torch.arange(T, dtype=torch.float32) * cfg.dt)[None].to(DEV)
+    with torch.no_grad():
+        gt, _ = sim(hill_map(cfg).to(DEV).unsqueeze(0), controls)
+
+    def grads(tape, scale):
+        sim.adjoint_tape = tape
+        z = torch.zeros(1, 256, 256, device=DEV, requires_grad=True)
+        fr = torch.full((1, 256, 256), 0.5, device=DEV, requires_grad=True)
+        c = controls.clone().requires_grad_(True)
+        st, _ = sim(z, c, friction=fr)
+        (scale * physics_loss(st, gt, ts, ts, 0.9)).backward()
+        return z.grad, fr.grad, c.grad
+
+    gz, gf, gc = grads(True, 1.0)
+    gz3, gf3, gc3 = grads(False, 1.0)
+    gz2, gf2, gc2 = grads(True, 2.0)
+    for a in (gz, gf, gc):
+        assert torch.isfinite(a).all()
+    assert gz.abs().max() > 0 and gf.abs().max() > 0 and gc.abs().max() > 0
+    assert rel_err(gz, gz3) < 1e-3 and rel_err(gf, gf3) < 1e-3 and rel_err(gc, gc3) < 1e-3          # (i)
+    assert torch.equal(gc[: B // 2], gc[B // 2:])                                                   # (ii)
+    assert rel_err(gz2, 2 * gz) < 1e-4 and rel_err(gf2, 2 * gf) < 1e-4 and rel_err(gc2, 2 * gc) < 1e-5   # (iii)
+    assert (gf != 0).float().mean() < 0.5                                                            # (iv)
