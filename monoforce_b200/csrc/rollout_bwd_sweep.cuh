@@ -14,8 +14,10 @@
 //       (kappa, fx, fy, cell) in shared memory and the next visit (step t-1) folds it into the point's
 //       private corner accumulators before anything else touches them.
 // The point loop is rolled (per-point state lives in shared memory, not in registers indexed by an unrolled
-// loop counter), so the kernel body is ~10x smaller than the three-pass kernel: no instruction-cache
-// stalls, fewer registers.
+// loop counter), so the kernel body is several times smaller than the three-pass kernel's: no instruction-cache
+// stalls.  Registers: the 36 running sums stay in registers; the carried state adjoint is parked in shared memory
+// while the point loop runs (MFB_SWEEP_PARK) and the warp-uniform operands of the step are re-read from shared
+// memory at every point (MFB_SWEEP_FRAME_SMEM) => 128 registers, 4 CTAs x 4 warps per SM.
 //
 // Map gradients: per sampling cell one 8-scalar record (d/dz and d/dfriction of the cell's four corners)
 // accumulated with two aligned 16-byte vector reductions; finalize_map_grads_kernel adds the records
