@@ -196,6 +196,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
     __shared__ SweepPoints<T> tab;
     __shared__ Quad<T> park_all[MFB_SWEEP_PARK ? kSweepWarps * 5 : 1];
     __shared__ Quad<T> frame_all[MFB_SWEEP_FRAME_SMEM ? kSweepWarps * 8 : 1];
+    __shared__ uint4 wconst_all[2 * kSweepWarps];  // per warp: [0] cell-table pointer (lo, hi), shared address of its cache, ppl; [1] zmap, fmap
     const int ppl = (a.N + 31) >> 5;
     const int slots = ppl * 32;
     fill_sweep_points(tab, a, slots);
@@ -291,6 +292,17 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
 
     T Cb_prev = (T)0;        // C_bar of the step visited last: its map-gradient share is applied at this visit
 
+    // Loop-invariant addresses the point loop needs.  At 128 registers the compiler re-derives them from the kernel
+    // parameters at every point (64-bit multiply-adds, ~25 instructions per point); one 16-byte shared load is cheaper.
+    if (lane == 0) {
+        const unsigned long long cp = (unsigned long long)cells;
+        const unsigned long long zp = (unsigned long long)zmap, fp = (unsigned long long)fmap;
+        wconst_all[2 * warp] = make_uint4((unsigned)cp, (unsigned)(cp >> 32), (unsigned)__cvta_generic_to_shared(cache), (unsigned)ppl);
+        wconst_all[2 * warp + 1] = make_uint4((unsigned)zp, (unsigned)(zp >> 32), (unsigned)fp, (unsigned)(fp >> 32));
+    }
+    __syncwarp();
+    const unsigned wconst_addr = (unsigned)__cvta_generic_to_shared(&wconst_all[2 * warp]);
+
     for (int t = n_steps - 1; t >= 0; --t) {
         Body<T> s;
         load_state(s, VARIANT == kOdeintEuler ? t : t - 1);
@@ -346,7 +358,11 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
         for (int k = 0; k < 12; ++k) kap[k] = (T)0;
 
 #pragma unroll kSweepUnroll
-        for (int j = 0; j < ppl; ++j) {
+        for (int j = 0;; ++j) {
+            uint4 wcst;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(wcst.x), "=r"(wcst.y), "=r"(wcst.z), "=r"(wcst.w) : "r"(wconst_addr));
+            const T* __restrict__ cells_w = reinterpret_cast<const T*>(((unsigned long long)wcst.y << 32) | wcst.x);
             const int slot = j * 32 + lane;
             const bool ok = slot < a.N;
             if (MFB_SWEEP_PREFETCH && gcell && j + 1 < ppl) {
@@ -378,7 +394,17 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                 }
             }
             PointEval<T> e;
-            eval_point(e, fl, px, py, pz, drv, side, ok, cells, zmap, fmap, H, W, a.inv_res, a.stiffness, a.damping);
+            eval_point<T, false>(e, fl, px, py, pz, drv, side, ok, cells_w, nullptr, nullptr, H, W, a.inv_res, a.stiffness, a.damping);
+            if (e.cell < 0) {
+                // off the map (rare): redo the point with the reference's clamped flat indices on the raw maps
+                uint4 mp;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];"
+                             : "=r"(mp.x), "=r"(mp.y), "=r"(mp.z), "=r"(mp.w) : "r"(wconst_addr));
+                eval_point<T, true>(e, fl, px, py, pz, drv, side, ok, cells_w,
+                                    reinterpret_cast<const T*>(((unsigned long long)mp.y << 32) | mp.x),
+                                    reinterpret_cast<const T*>(((unsigned long long)mp.w << 32) | mp.z),
+                                    H, W, a.inv_res, a.stiffness, a.damping);
+            }
             const T n0 = e.rec[4], n1 = e.rec[5], n2 = e.rec[6];
             const T fx = e.fx, fy = e.fy;
             const T r0 = e.r[0], r1 = e.r[1], r2 = e.r[2];
@@ -471,7 +497,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             const T fy_b = zv_b * dz_dfy + mu_b * (e.rec[9] + fx * e.rec[11]);
 
             if (gcell && ok) {
-                Quad<T>* const rec = cache + 3 * slot;
+                Quad<T>* const rec = reinterpret_cast<Quad<T>*>(__cvta_shared_to_generic(wcst.z)) + 3 * slot;
                 const Quad<T> pend = quad_load(rec + 2);
                 const bool on_map = e.cell >= 0;
                 {   // park this visit's (kappa, fx, fy, cell); off-map points keep their raw grid coordinates instead
@@ -534,6 +560,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                 kap[6] += u1 * px; kap[7] += u1 * py; kap[8] += u1 * pz;
                 kap[9] += kk * px; kap[10] += kk * py; kap[11] += kk * pz;
             }
+            if (j + 1 >= (int)wcst.w) break;
         }
 
         if (MFB_SWEEP_FRAME_SMEM) {
