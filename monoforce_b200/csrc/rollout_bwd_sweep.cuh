@@ -77,6 +77,50 @@ __device__ __noinline__ void fixup_off_map(T* __restrict__ gz, T coef, T ggx, T 
                        (T)0, (T)0, (T)0, (T)0);
 }
 
+// 16-byte shared-memory loads at [base + OFF] (32-bit shared address, compile-time offset); volatile: re-read at every use
+template <int OFF>
+__device__ __forceinline__ Quad<float> lds_quad(uint32_t base, float) {
+    Quad<float> q;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                 : "=f"(q.v[0]), "=f"(q.v[1]), "=f"(q.v[2]), "=f"(q.v[3]) : "r"(base), "n"(OFF));
+    return q;
+}
+template <int OFF>
+__device__ __forceinline__ Quad<double> lds_quad(uint32_t base, double) {
+    Quad<double> q;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(q.v[0]), "=d"(q.v[1]) : "r"(base), "n"(OFF));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(q.v[2]), "=d"(q.v[3]) : "r"(base), "n"(OFF + 16));
+    return q;
+}
+template <int OFF>
+__device__ __forceinline__ uint4 lds_u4(uint32_t base) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base), "n"(OFF));
+    return v;
+}
+
+// raw-map pointers fetched from the warp's shared area only when a point is off the map
+template <typename T>
+struct LazyMaps {
+    uint32_t area_s;
+    __device__ __forceinline__ const T* z() const {
+        const uint4 mp = lds_u4<16>(area_s);
+        return reinterpret_cast<const T*>(((unsigned long long)mp.y << 32) | mp.x);
+    }
+    __device__ __forceinline__ const T* mu() const {
+        const uint4 mp = lds_u4<16>(area_s);
+        return reinterpret_cast<const T*>(((unsigned long long)mp.w << 32) | mp.z);
+    }
+};
+
+// everything one warp keeps in static shared memory, addressed from ONE pinned 32-bit base
+template <typename T>
+struct __align__(16) SweepWarpArea {
+    uint4 wc[2];         // [0] cell-table pointer (lo, hi), shared address of the warp's cache, ppl | N << 8 ; [1] zmap, fmap pointers
+    Quad<T> fr[8];       // warp-uniform operands of the current step (MFB_SWEEP_FRAME_SMEM)
+    Quad<T> pk[5];       // carried state adjoint while the point loop runs (MFB_SWEEP_PARK)
+};
+
 template <typename T>
 __device__ __forceinline__ void flush_cell(T* __restrict__ gcell, int cell, const Quad<T>& qz, const Quad<T>& qm) {
     T* p = gcell + (long long)cell * kGradRec;
@@ -194,9 +238,8 @@ __global__ void __launch_bounds__(kSweepWarps * 32, sizeof(T) == 4 ? MFB_SWEEP_M
 rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
     static_assert(!(VARIANT == kOdeintEuler && HAS_FGRAD), "odeint + force gradients: use the three-pass kernel");
     __shared__ SweepPoints<T> tab;
-    __shared__ Quad<T> park_all[MFB_SWEEP_PARK ? kSweepWarps * 5 : 1];
-    __shared__ Quad<T> frame_all[MFB_SWEEP_FRAME_SMEM ? kSweepWarps * 8 : 1];
-    __shared__ uint4 wconst_all[2 * kSweepWarps];  // per warp: [0] cell-table pointer (lo, hi), shared address of its cache, ppl; [1] zmap, fmap
+    __shared__ SweepWarpArea<T> area_all[kSweepWarps];
+    constexpr int kOffFr = (int)offsetof(SweepWarpArea<T>, fr), kQ = (int)sizeof(Quad<T>);
     const int ppl = (a.N + 31) >> 5;
     const int slots = ppl * 32;
     fill_sweep_points(tab, a, slots);
@@ -297,11 +340,13 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
     if (lane == 0) {
         const unsigned long long cp = (unsigned long long)cells;
         const unsigned long long zp = (unsigned long long)zmap, fp = (unsigned long long)fmap;
-        wconst_all[2 * warp] = make_uint4((unsigned)cp, (unsigned)(cp >> 32), (unsigned)__cvta_generic_to_shared(cache), (unsigned)ppl);
-        wconst_all[2 * warp + 1] = make_uint4((unsigned)zp, (unsigned)(zp >> 32), (unsigned)fp, (unsigned)(fp >> 32));
+        area_all[warp].wc[0] = make_uint4((unsigned)cp, (unsigned)(cp >> 32), (unsigned)__cvta_generic_to_shared(cache),
+                                          (unsigned)ppl | ((unsigned)a.N << 8));
+        area_all[warp].wc[1] = make_uint4((unsigned)zp, (unsigned)(zp >> 32), (unsigned)fp, (unsigned)(fp >> 32));
     }
     __syncwarp();
-    const unsigned wconst_addr = (unsigned)__cvta_generic_to_shared(&wconst_all[2 * warp]);
+    unsigned area_s = (unsigned)__cvta_generic_to_shared(&area_all[warp]);
+    asm volatile("mov.u32 %0, %0;" : "+r"(area_s));        // opaque: keep the base in a register, do not re-derive it
 
     for (int t = n_steps - 1; t >= 0; --t) {
         Body<T> s;
@@ -325,7 +370,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
         const T hd_norm = Mth<T>::sqrt_rn(s.R[0] * s.R[0] + s.R[3] * s.R[3] + s.R[6] * s.R[6]);
 
         if (MFB_SWEEP_PARK) {
-            Quad<T>* pk = park_all + warp * 5;
+            Quad<T>* pk = area_all[warp].pk;
             Quad<T> q;
             q.v[0] = xb[0]; q.v[1] = xb[1]; q.v[2] = xb[2]; q.v[3] = vb[0]; quad_store(pk + 0, q);
             q.v[0] = vb[1]; q.v[1] = vb[2]; q.v[2] = wb[0]; q.v[3] = wb[1]; quad_store(pk + 1, q);
@@ -334,7 +379,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             q.v[0] = Rb[7]; q.v[1] = Rb[8]; q.v[2] = hd_norm; q.v[3] = (T)0; quad_store(pk + 4, q);
             __syncwarp();
         }
-        Quad<T>* const fr = frame_all + (MFB_SWEEP_FRAME_SMEM ? warp * 8 : 0);
+        Quad<T>* const fr = area_all[warp].fr;
         if (MFB_SWEEP_FRAME_SMEM) {
             Quad<T> q;
             q.v[0] = f.v[0]; q.v[1] = f.v[1]; q.v[2] = f.v[2]; q.v[3] = f.w[0]; quad_store(fr + 0, q);
@@ -359,12 +404,10 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
 
 #pragma unroll kSweepUnroll
         for (int j = 0;; ++j) {
-            uint4 wcst;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(wcst.x), "=r"(wcst.y), "=r"(wcst.z), "=r"(wcst.w) : "r"(wconst_addr));
+            const uint4 wcst = lds_u4<0>(area_s);
             const T* __restrict__ cells_w = reinterpret_cast<const T*>(((unsigned long long)wcst.y << 32) | wcst.x);
             const int slot = j * 32 + lane;
-            const bool ok = slot < a.N;
+            const bool ok = slot < (int)(wcst.w >> 8);
             if (MFB_SWEEP_PREFETCH && gcell && j + 1 < ppl) {
                 // the NEXT point's cell record: with 16 warps per SM the table does not stay in L1 between two visits, but
                 // a point rarely leaves its cell within one step, so the cell it was in at its previous visit (parked in
@@ -379,7 +422,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             T L_invC = invC, L_Cb_prev = Cb_prev, L_tq[3] = {tq_b[0], tq_b[1], tq_b[2]}, L_fs[3] = {fs_b0, fs_b1, fs_b2};
             T L_w[3] = {s.w[0], s.w[1], s.w[2]};
             if (MFB_SWEEP_FRAME_SMEM) {
-                const Quad<T> q0 = quad_load_pinned(fr + 0), q1 = quad_load_pinned(fr + 1), q2 = quad_load_pinned(fr + 2);
+                const Quad<T> q0 = lds_quad<kOffFr + 0 * kQ>(area_s, (T)0), q1 = lds_quad<kOffFr + 1 * kQ>(area_s, (T)0), q2 = lds_quad<kOffFr + 2 * kQ>(area_s, (T)0);
                 fl.v[0] = q0.v[0]; fl.v[1] = q0.v[1]; fl.v[2] = q0.v[2];
                 fl.w[0] = q0.v[3]; fl.w[1] = q1.v[0]; fl.w[2] = q1.v[1];
                 fl.uv = q1.v[2]; fl.uw = q1.v[3];
@@ -387,29 +430,20 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                 L_invC = q2.v[3];
                 L_w[0] = fl.w[0]; L_w[1] = fl.w[1]; L_w[2] = fl.w[2];
                 if (MFB_SWEEP_FRAME_SMEM >= 2) {
-                    const Quad<T> q5 = quad_load_pinned(fr + 5), q6 = quad_load_pinned(fr + 6), q7 = quad_load_pinned(fr + 7);
+                    const Quad<T> q5 = lds_quad<kOffFr + 5 * kQ>(area_s, (T)0), q6 = lds_quad<kOffFr + 6 * kQ>(area_s, (T)0), q7 = lds_quad<kOffFr + 7 * kQ>(area_s, (T)0);
                     fl.R[0] = q5.v[0]; fl.R[1] = q5.v[1]; fl.R[2] = q5.v[2]; fl.R[3] = q5.v[3];
                     fl.R[4] = q6.v[0]; fl.R[5] = q6.v[1]; fl.R[6] = q6.v[2]; fl.R[7] = q6.v[3];
                     fl.R[8] = q7.v[0]; fl.ox = q7.v[1]; fl.oy = q7.v[2];
                 }
             }
             PointEval<T> e;
-            eval_point<T, false>(e, fl, px, py, pz, drv, side, ok, cells_w, nullptr, nullptr, H, W, a.inv_res, a.stiffness, a.damping);
-            if (e.cell < 0) {
-                // off the map (rare): redo the point with the reference's clamped flat indices on the raw maps
-                uint4 mp;
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+16];"
-                             : "=r"(mp.x), "=r"(mp.y), "=r"(mp.z), "=r"(mp.w) : "r"(wconst_addr));
-                eval_point<T, true>(e, fl, px, py, pz, drv, side, ok, cells_w,
-                                    reinterpret_cast<const T*>(((unsigned long long)mp.y << 32) | mp.x),
-                                    reinterpret_cast<const T*>(((unsigned long long)mp.w << 32) | mp.z),
-                                    H, W, a.inv_res, a.stiffness, a.damping);
-            }
+            eval_point_maps<T, true>(e, fl, px, py, pz, drv, side, ok, cells_w, LazyMaps<T>{area_s}, H, W, a.inv_res, a.stiffness,
+                                     a.damping);
             const T n0 = e.rec[4], n1 = e.rec[5], n2 = e.rec[6];
             const T fx = e.fx, fy = e.fy;
             const T r0 = e.r[0], r1 = e.r[1], r2 = e.r[2];
             if (MFB_SWEEP_FRAME_SMEM) {
-                const Quad<T> q3 = quad_load_pinned(fr + 3), q4 = quad_load_pinned(fr + 4);
+                const Quad<T> q3 = lds_quad<kOffFr + 3 * kQ>(area_s, (T)0), q4 = lds_quad<kOffFr + 4 * kQ>(area_s, (T)0);
                 L_tq[0] = q3.v[0]; L_tq[1] = q3.v[1]; L_tq[2] = q3.v[2];
                 L_fs[0] = q3.v[3]; L_fs[1] = q4.v[0]; L_fs[2] = q4.v[1];
                 L_Cb_prev = q4.v[2];
@@ -560,18 +594,18 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                 kap[6] += u1 * px; kap[7] += u1 * py; kap[8] += u1 * pz;
                 kap[9] += kk * px; kap[10] += kk * py; kap[11] += kk * pz;
             }
-            if (j + 1 >= (int)wcst.w) break;
+            if (j + 1 >= (int)(wcst.w & 0xffu)) break;
         }
 
         if (MFB_SWEEP_FRAME_SMEM) {
             // bring the operands the epilogue of the step needs back from shared memory (they did not occupy registers meanwhile)
-            const Quad<T> q0 = quad_load_pinned(fr + 0), q1 = quad_load_pinned(fr + 1), q2 = quad_load_pinned(fr + 2);
+            const Quad<T> q0 = lds_quad<kOffFr + 0 * kQ>(area_s, (T)0), q1 = lds_quad<kOffFr + 1 * kQ>(area_s, (T)0), q2 = lds_quad<kOffFr + 2 * kQ>(area_s, (T)0);
             s.w[0] = q0.v[3]; s.w[1] = q1.v[0]; s.w[2] = q1.v[1];
             f.hd[0] = q2.v[0]; f.hd[1] = q2.v[1]; f.hd[2] = q2.v[2];
         }
         T hd_nrm = hd_norm;
         if (MFB_SWEEP_PARK) {
-            const Quad<T>* pk = park_all + warp * 5;
+            const Quad<T>* pk = area_all[warp].pk;
             Quad<T> q;
             q = quad_load(pk + 0); xb[0] = q.v[0]; xb[1] = q.v[1]; xb[2] = q.v[2]; vb[0] = q.v[3];
             q = quad_load(pk + 1); vb[1] = q.v[0]; vb[2] = q.v[1]; wb[0] = q.v[2]; wb[1] = q.v[3];
@@ -581,7 +615,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             __syncwarp();
         }
         // C_bar first (one butterfly), so that every lane can close its kappa channel before the big reduction
-        const T C_b = -warp_sum(acc[23]) * (MFB_SWEEP_FRAME_SMEM ? quad_load_pinned(fr + 2).v[3] : invC);
+        const T C_b = -warp_sum(acc[23]) * (MFB_SWEEP_FRAME_SMEM ? lds_quad<kOffFr + 2 * kQ>(area_s, (T)0).v[3] : invC);
         Cb_prev = C_b;
 #pragma unroll
         for (int i = 0; i < 3; ++i) acc[i] += C_b * kap[i];

@@ -356,10 +356,19 @@ struct PointEval {
 // `cells` / `zmap` / `fmap` are already offset to this trajectory's map.
 // PATCH_OFF_MAP = false: branch-free fast path; an off-map point (o.cell == -1) is evaluated on cell 0's record and the
 // caller must redo the step with PATCH_OFF_MAP = true if any lane reports one (rare).
-template <typename T, bool PATCH_OFF_MAP = true>
-__device__ __forceinline__ void eval_point(PointEval<T>& o, const StepFrame<T>& f, T px, T py, T pz, T drv, T side,
-                                           bool valid, const T* __restrict__ cells, const T* __restrict__ zmap,
-                                           const T* __restrict__ fmap, int H, int W, T inv_res, T stiffness, T damping) {
+// Raw-map pointers for the off-map path; `Maps` is any type with z() / mu() so that a caller can fetch them lazily
+// (the single-sweep adjoint keeps them in shared memory: they are needed by one point in thousands).
+template <typename T>
+struct MapPtrs {
+    const T* zp; const T* mp;
+    __device__ __forceinline__ const T* z() const { return zp; }
+    __device__ __forceinline__ const T* mu() const { return mp; }
+};
+
+template <typename T, bool PATCH_OFF_MAP, class Maps>
+__device__ __forceinline__ void eval_point_maps(PointEval<T>& o, const StepFrame<T>& f, T px, T py, T pz, T drv, T side,
+                                                bool valid, const T* __restrict__ cells, const Maps& maps, int H, int W,
+                                                T inv_res, T stiffness, T damping) {
     // r = R p ; V = v + w x r                                                  dphysics.py:200-204
     o.r[0] = f.R[0] * px + f.R[1] * py + f.R[2] * pz;
     o.r[1] = f.R[3] * px + f.R[4] * py + f.R[5] * pz;
@@ -384,7 +393,7 @@ __device__ __forceinline__ void eval_point(PointEval<T>& o, const StepFrame<T>& 
     if (PATCH_OFF_MAP && !on_map) {
         // the record goes through a local buffer so that o.rec itself stays in registers
         T tmp[kCellRec + 2];
-        sample_off_map(zmap, fmap, gx, gy, H, W, inv_res, tmp);
+        sample_off_map(maps.z(), maps.mu(), gx, gy, H, W, inv_res, tmp);
 #pragma unroll
         for (int k = 0; k < kCellRec; ++k) o.rec[k] = tmp[k];
         o.fx = tmp[kCellRec]; o.fy = tmp[kCellRec + 1];
@@ -405,6 +414,14 @@ __device__ __forceinline__ void eval_point(PointEval<T>& o, const StepFrame<T>& 
     o.d[0] = o.mu * o.e[0]; o.d[1] = o.mu * o.e[1]; o.d[2] = o.mu * o.e[2];
     o.dn = o.d[0] * n0 + o.d[1] * n1 + o.d[2] * n2;
     o.sl[0] = o.d[0] - o.dn * n0; o.sl[1] = o.d[1] - o.dn * n1; o.sl[2] = o.d[2] - o.dn * n2;
+}
+
+template <typename T, bool PATCH_OFF_MAP = true>
+__device__ __forceinline__ void eval_point(PointEval<T>& o, const StepFrame<T>& f, T px, T py, T pz, T drv, T side,
+                                           bool valid, const T* __restrict__ cells, const T* __restrict__ zmap,
+                                           const T* __restrict__ fmap, int H, int W, T inv_res, T stiffness, T damping) {
+    eval_point_maps<T, PATCH_OFF_MAP>(o, f, px, py, pz, drv, side, valid, cells, MapPtrs<T>{zmap, fmap}, H, W, inv_res,
+                                      stiffness, damping);
 }
 
 // ------------------------------------------------------------------------------------------
