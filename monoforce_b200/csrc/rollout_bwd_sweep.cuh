@@ -442,6 +442,8 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             const T n0 = e.rec[4], n1 = e.rec[5], n2 = e.rec[6];
             const T fx = e.fx, fy = e.fy;
             const T r0 = e.r[0], r1 = e.r[1], r2 = e.r[2];
+            int cell_p = e.cell;
+            asm volatile("mov.s32 %0, %0;" : "+r"(cell_p));     // opaque: or the cell index is re-derived (2 F2I + 7) at each of its 3 uses
             if (MFB_SWEEP_FRAME_SMEM) {
                 const Quad<T> q3 = lds_quad<kOffFr + 3 * kQ>(area_s, (T)0), q4 = lds_quad<kOffFr + 4 * kQ>(area_s, (T)0);
                 L_tq[0] = q3.v[0]; L_tq[1] = q3.v[1]; L_tq[2] = q3.v[2];
@@ -463,9 +465,9 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
 
             // ---- phase 2 reversed ----
             // torque = sum r x F :  F_bar += tq_bar x r ;  r_bar += F x tq_bar
-            T Frb0 = L_fs[0] + (L_tq[1] * r2 - L_tq[2] * r1);
-            T Frb1 = L_fs[1] + (L_tq[2] * r0 - L_tq[0] * r2);
-            T Frb2 = L_fs[2] + (L_tq[0] * r1 - L_tq[1] * r0);
+            T Frb0 = fma(L_tq[1], r2, fma(-L_tq[2], r1, L_fs[0]));
+            T Frb1 = fma(L_tq[2], r0, fma(-L_tq[0], r2, L_fs[1]));
+            T Frb2 = fma(L_tq[0], r1, fma(-L_tq[1], r0, L_fs[2]));
             T Ftb0 = Frb0, Ftb1 = Frb1, Ftb2 = Frb2;
             if (HAS_FGRAD) {
                 const long long o = ((long long)b * a.nT + rec) * rowF + (long long)slot * 3;
@@ -498,7 +500,8 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             const T cw_b = sc_b * e.sp;
             // slip = d - dn n ; dn = d . n
             const T dn_b = -(sb0 * n0 + sb1 * n1 + sb2 * n2);
-            nb0 += -e.dn * sb0 + dn_b * e.d[0]; nb1 += -e.dn * sb1 + dn_b * e.d[1]; nb2 += -e.dn * sb2 + dn_b * e.d[2];
+            nb0 = fma(dn_b, e.d[0], fma(-e.dn, sb0, nb0)); nb1 = fma(dn_b, e.d[1], fma(-e.dn, sb1, nb1));
+            nb2 = fma(dn_b, e.d[2], fma(-e.dn, sb2, nb2));
             const T db0 = sb0 + dn_b * n0, db1 = sb1 + dn_b * n1, db2 = sb2 + dn_b * n2;
             // d = mu e ; e = tau hd - V
             const T mu_b = db0 * e.e[0] + db1 * e.e[1] + db2 * e.e[2];
@@ -533,17 +536,17 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             if (gcell && ok) {
                 Quad<T>* const rec = reinterpret_cast<Quad<T>*>(__cvta_shared_to_generic(wcst.z)) + 3 * slot;
                 const Quad<T> pend = quad_load(rec + 2);
-                const bool on_map = e.cell >= 0;
+                const bool on_map = cell_p >= 0;
                 {   // park this visit's (kappa, fx, fy, cell); off-map points keep their raw grid coordinates instead
                     Quad<T> np;
                     np.v[0] = kappa;
                     np.v[1] = on_map ? fx : r0 * a.inv_res + fl.ox;
                     np.v[2] = on_map ? fy : r1 * a.inv_res + fl.oy;
-                    np.v[3] = pack_cell(e.cell, (T)0);
+                    np.v[3] = pack_cell(cell_p, (T)0);
                     quad_store(rec + 2, np);
                 }
                 const int cur = unpack_cell(pend.v[3]);
-                const bool same = cur == e.cell;
+                const bool same = cur == cell_p;
                 Quad<T> qz = quad_load(rec), qm = quad_load(rec + 1);
                 // (1) the previous visit's kappa-channel share, now that its C_bar is known
                 const T coef = -L_Cb_prev * pend.v[0];
@@ -573,14 +576,15 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             // grid coordinate -> world point ; V = v + w x r ; P = r + x ; r = R p
             const T ires = a.inv_res;
             const T Pb0 = fx_b * ires, Pb1 = fy_b * ires, Pb2 = dh_b;
-            T rb0 = ab0 + Pb0 + (Vb1 * L_w[2] - Vb2 * L_w[1]);
-            T rb1 = ab1 + Pb1 + (Vb2 * L_w[0] - Vb0 * L_w[2]);
-            T rb2 = ab2 + Pb2 + (Vb0 * L_w[1] - Vb1 * L_w[0]);
+            T rb0 = fma(Vb1, L_w[2], fma(-Vb2, L_w[1], ab0 + Pb0));
+            T rb1 = fma(Vb2, L_w[0], fma(-Vb0, L_w[2], ab1 + Pb1));
+            T rb2 = fma(Vb0, L_w[1], fma(-Vb1, L_w[0], ab2 + Pb2));
             if (!ok) { rb0 = rb1 = rb2 = (T)0; Vb0 = Vb1 = Vb2 = (T)0; }
             const T okf = ok ? (T)1 : (T)0;
             acc[0] += okf * Pb0; acc[1] += okf * Pb1; acc[2] += okf * Pb2;
             acc[3] += Vb0; acc[4] += Vb1; acc[5] += Vb2;
-            acc[6] += r1 * Vb2 - r2 * Vb1; acc[7] += r2 * Vb0 - r0 * Vb2; acc[8] += r0 * Vb1 - r1 * Vb0;
+            acc[6] = fma(r1, Vb2, fma(-r2, Vb1, acc[6])); acc[7] = fma(r2, Vb0, fma(-r0, Vb2, acc[7]));
+            acc[8] = fma(r0, Vb1, fma(-r1, Vb0, acc[8]));
             acc[9] += rb0 * px;  acc[10] += rb0 * py; acc[11] += rb0 * pz;
             acc[12] += rb1 * px; acc[13] += rb1 * py; acc[14] += rb1 * pz;
             acc[15] += rb2 * px; acc[16] += rb2 * py; acc[17] += rb2 * pz;
