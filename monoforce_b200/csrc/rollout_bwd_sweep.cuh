@@ -77,28 +77,6 @@ __device__ __noinline__ void fixup_off_map(T* __restrict__ gz, T coef, T ggx, T 
                        (T)0, (T)0, (T)0, (T)0);
 }
 
-// 16-byte shared-memory loads at [base + OFF] (32-bit shared address, compile-time offset); volatile: re-read at every use
-template <int OFF>
-__device__ __forceinline__ Quad<float> lds_quad(uint32_t base, float) {
-    Quad<float> q;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
-                 : "=f"(q.v[0]), "=f"(q.v[1]), "=f"(q.v[2]), "=f"(q.v[3]) : "r"(base), "n"(OFF));
-    return q;
-}
-template <int OFF>
-__device__ __forceinline__ Quad<double> lds_quad(uint32_t base, double) {
-    Quad<double> q;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(q.v[0]), "=d"(q.v[1]) : "r"(base), "n"(OFF));
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(q.v[2]), "=d"(q.v[3]) : "r"(base), "n"(OFF + 16));
-    return q;
-}
-template <int OFF>
-__device__ __forceinline__ uint4 lds_u4(uint32_t base) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base), "n"(OFF));
-    return v;
-}
-
 // raw-map pointers fetched from the warp's shared area only when a point is off the map
 template <typename T>
 struct LazyMaps {

@@ -20,6 +20,10 @@ constexpr int kFwdWarps = 4;   // trajectories per CTA
 #ifndef MFB_FWD_REDO
 #define MFB_FWD_REDO 1      // 1: branch-free phase 1 + whole-step redo when a point is off the map
 #endif
+#ifndef MFB_FWD_PTRS_SMEM
+#define MFB_FWD_PTRS_SMEM 0   // 1: per-trajectory output pointers wait in shared memory instead of being re-derived from the kernel
+                              // parameters every step.  Measured: 0 -> 2.72 ms, 1 -> 2.86 ms (more spills), so off
+#endif
 #ifndef MFB_FWD_MINB
 #define MFB_FWD_MINB 4        // resident CTAs per SM the fp32 kernel is compiled for (128 registers)
 #endif
@@ -133,17 +137,41 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
     T* __restrict__ Xd_b = a.Xds + (long long)b * a.nT * 3;
     T* __restrict__ Rs_b = a.Rs + (long long)b * a.nT * 9;
     T* __restrict__ Om_b = a.Oms + (long long)b * a.nT * 3;
+    T* __restrict__ Cs_b = a.Csum ? a.Csum + (long long)b * a.nT : nullptr;
+
+    // [0] (Xs_b, Xd_b)  [1] (Rs_b, Om_b)  [2] (Fs_b, Ff_b)  [3] (controls, contact_sum) of this warp's trajectory
+    __shared__ uint4 fptr_all[MFB_FWD_PTRS_SMEM ? kFwdWarps * 4 : 1];
+    unsigned fptr_s = 0;
+    if (MFB_FWD_PTRS_SMEM) {
+        uint4* fp = fptr_all + (threadIdx.x >> 5) * 4;
+        if (lane == 0) {
+            auto pk = [](const void* p0, const void* p1) {
+                const unsigned long long u0 = (unsigned long long)p0, u1 = (unsigned long long)p1;
+                return make_uint4((unsigned)u0, (unsigned)(u0 >> 32), (unsigned)u1, (unsigned)(u1 >> 32));
+            };
+            fp[0] = pk(Xs_b, Xd_b); fp[1] = pk(Rs_b, Om_b); fp[2] = pk(Fs_b, Ff_b); fp[3] = pk(ctrl, Cs_b);
+        }
+        __syncwarp();
+        fptr_s = (unsigned)__cvta_generic_to_shared(fp);
+        asm volatile("mov.u32 %0, %0;" : "+r"(fptr_s));
+    }
 
     auto record_state = [&](int t) {
         if (lane == 0) {
+            T *pXs = Xs_b, *pXd = Xd_b, *pRs = Rs_b, *pOm = Om_b;
+            if (MFB_FWD_PTRS_SMEM) {
+                const uint4 p0 = lds_u4<0>(fptr_s), p1 = lds_u4<16>(fptr_s);
+                pXs = reinterpret_cast<T*>(u64_of(p0.x, p0.y)); pXd = reinterpret_cast<T*>(u64_of(p0.z, p0.w));
+                pRs = reinterpret_cast<T*>(u64_of(p1.x, p1.y)); pOm = reinterpret_cast<T*>(u64_of(p1.z, p1.w));
+            }
             // Xs = x + R[:,2] * delta_h                                          dphysics.py:587-589
-            Xs_b[t * 3 + 0] = s.x[0] + s.R[2] * a.delta_h;
-            Xs_b[t * 3 + 1] = s.x[1] + s.R[5] * a.delta_h;
-            Xs_b[t * 3 + 2] = s.x[2] + s.R[8] * a.delta_h;
+            pXs[t * 3 + 0] = s.x[0] + s.R[2] * a.delta_h;
+            pXs[t * 3 + 1] = s.x[1] + s.R[5] * a.delta_h;
+            pXs[t * 3 + 2] = s.x[2] + s.R[8] * a.delta_h;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) { Xd_b[t * 3 + i] = s.v[i]; Om_b[t * 3 + i] = s.w[i]; }
+            for (int i = 0; i < 3; ++i) { pXd[t * 3 + i] = s.v[i]; pOm[t * 3 + i] = s.w[i]; }
 #pragma unroll
-            for (int i = 0; i < 9; ++i) Rs_b[t * 9 + i] = s.R[i];
+            for (int i = 0; i < 9; ++i) pRs[t * 9 + i] = s.R[i];
         }
     };
 
@@ -173,7 +201,11 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
     for (int t = 0; t < n_steps; ++t) {
         // prefetch next controls
         T uv_n = uv, uw_n = uw;
-        if (t + 1 < a.nT) { uv_n = ctrl[(t + 1) * 2]; uw_n = ctrl[(t + 1) * 2 + 1]; }
+        if (t + 1 < a.nT) {
+            const T* cp = ctrl;
+            if (MFB_FWD_PTRS_SMEM) { const uint4 p3 = lds_u4<48>(fptr_s); cp = reinterpret_cast<const T*>(u64_of(p3.x, p3.y)); }
+            uv_n = cp[(t + 1) * 2]; uw_n = cp[(t + 1) * 2 + 1];
+        }
 
         StepFrame<T> f;
         make_frame(f, s, uv, uw, a.d_max, a.res, a.inv_res);
@@ -234,7 +266,11 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
 
         C = warp_sum(C);
         const T invC = Mth<T>::rcp(C);
-        if (a.Csum && lane == 0) a.Csum[(long long)b * a.nT + t] = C;      // tape of the single-sweep adjoint
+        if (lane == 0) {                                                    // tape of the single-sweep adjoint
+            T* cs = Cs_b;
+            if (MFB_FWD_PTRS_SMEM) { const uint4 p3 = lds_u4<48>(fptr_s); cs = reinterpret_cast<T*>(u64_of(p3.z, p3.w)); }
+            if (cs) cs[t] = C;
+        }
 
         T sum[6];
 #pragma unroll
@@ -245,8 +281,16 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
 
         // row pointers are re-derived from t every step: carrying them across the loop costs 5 registers and measured
         // +0.19 ms (spills) at 128 registers / thread
-        T* __restrict__ Fs_t = FORCES ? Fs_b + (long long)(VARIANT == kOdeintEuler ? t + 1 : t) * rowF : nullptr;
-        T* __restrict__ Ff_t = FORCES ? Ff_b + (long long)(VARIANT == kOdeintEuler ? t + 1 : t) * rowF : nullptr;
+        T *Fs_t = nullptr, *Ff_t = nullptr;
+        if (FORCES) {
+            T *pFs = Fs_b, *pFf = Ff_b;
+            if (MFB_FWD_PTRS_SMEM) {
+                const uint4 p2 = lds_u4<32>(fptr_s);
+                pFs = reinterpret_cast<T*>(u64_of(p2.x, p2.y)); pFf = reinterpret_cast<T*>(u64_of(p2.z, p2.w));
+            }
+            Fs_t = pFs + (long long)(VARIANT == kOdeintEuler ? t + 1 : t) * rowF;
+            Ff_t = pFf + (long long)(VARIANT == kOdeintEuler ? t + 1 : t) * rowF;
+        }
         // phase of the row start inside a 16-byte line (both tensors share it: same shape, 16-byte aligned bases)
         const int phase = FORCES ? (int)((((long long)b * a.nT + (VARIANT == kOdeintEuler ? t + 1 : t)) * rowF) &
                                          (RowStage<T>::kPer16 - 1)) : 0;
