@@ -74,9 +74,8 @@ __device__ __forceinline__ T gate(T grad, T val, T lim) {   // backward of clamp
 // adjoint of E(w) = I + sn K + c1 (k k^T - |k|^2 I) (see rodrigues_right); accumulates into wb
 template <typename T>
 __device__ __forceinline__ void rodrigues_right_bwd(const T* w, T dt, const T* Eb, T* wb) {
-    const T th = Mth<T>::sqrt_rn(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-    const T thc = Mth<T>::fmax_(th, (T)1e-6);
-    const T inv = (T)1 / thc;
+    T th, inv;         // |w| and 1 / max(|w|, 1e-6), the same way the forward forms them (one rsqrt in fp32)
+    Mth<T>::norm_and_inv(w[0] * w[0] + w[1] * w[1] + w[2] * w[2], &th, &inv);
     const T k0 = w[0] * inv, k1 = w[1] * inv, k2 = w[2] * inv;
     T sn, c1;
     sin_versin(th * dt, &sn, &c1);
@@ -101,7 +100,7 @@ __device__ __forceinline__ void rodrigues_right_bwd(const T* w, T dt, const T* E
     const T inv_b = kb0 * w[0] + kb1 * w[1] + kb2 * w[2];
     if (th >= (T)1e-6) th_b -= inv_b * inv * inv;
     if (th > (T)0) {
-        const T sc = th_b / th;
+        const T sc = th >= (T)1e-6 ? th_b * inv : th_b / th;
         wb[0] += sc * w[0]; wb[1] += sc * w[1]; wb[2] += sc * w[2];
     }
 }

@@ -145,8 +145,8 @@ __device__ __forceinline__ void reverse_update(const RolloutArgs<T>& a, const Bo
         // R' = R E(w'):  E_bar = R^T R'_bar ; R_bar = R'_bar E^T                     dphysics.py:290-324
         T Eb[9], E[9];
         {
-            const T th = Mth<T>::sqrt_rn(w_post[0] * w_post[0] + w_post[1] * w_post[1] + w_post[2] * w_post[2]);
-            const T inv = Mth<T>::inv(Mth<T>::fmax_(th, (T)1e-6));
+            T th, inv;
+            Mth<T>::norm_and_inv(w_post[0] * w_post[0] + w_post[1] * w_post[1] + w_post[2] * w_post[2], &th, &inv);
             const T k0 = w_post[0] * inv, k1 = w_post[1] * inv, k2 = w_post[2] * inv;
             T sn, c1;
             sin_versin(th * a.dt, &sn, &c1);
