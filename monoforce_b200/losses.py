@@ -64,7 +64,9 @@ class _FusedPhysicsLoss(torch.autograd.Function):
         return (None if g is None else g * grad_out), None, None, None, None
 
 
-def _torch_physics_loss(X_pred, X, pred_ts, gt_ts, gamma):
+def _host_physics_loss(X_pred, X, pred_ts, gt_ts, gamma):
+    """HOST tensors only: the reference's definition written with torch ops, for the CPU unit tests of the definition
+    (tests/test_host_logic.py).  CUDA tensors never take this path (see physics_loss)."""
     if _same_grid(pred_ts, gt_ts) and X_pred.shape[1] == gt_ts.shape[-1]:
         X_pred_gt_ts = X_pred
     else:
@@ -79,6 +81,11 @@ def physics_loss(states_pred, states_gt, pred_ts, gt_ts, gamma=0.9, rotation_los
         raise NotImplementedError("rotation_loss=True is not used by any caller on the hot path")
     X = states_gt[0]
     X_pred = states_pred[0]
-    if X_pred.is_cuda and X_pred.dtype in (torch.float32, torch.float64) and not X.requires_grad:
+    if X_pred.is_cuda:
+        if X_pred.dtype not in (torch.float32, torch.float64):
+            raise TypeError(f"physics_loss supports float32 / float64 on CUDA, got {X_pred.dtype}")
+        if X.requires_grad:
+            raise NotImplementedError("physics_loss: gradients w.r.t. the ground-truth states are not provided by the "
+                                      "fused kernel (no caller of the reference differentiates them)")
         return _FusedPhysicsLoss.apply(X_pred, X, pred_ts, gt_ts, gamma)
-    return _torch_physics_loss(X_pred, X, pred_ts, gt_ts, gamma)
+    return _host_physics_loss(X_pred, X, pred_ts, gt_ts, gamma)
