@@ -23,10 +23,11 @@ import ctypes as C
 
 import torch
 from torch import nn
+from torch.nn import functional as F
 from torchvision.models.resnet import resnet18
 
 from . import _lib, ops
-from .efficientnet import EfficientNet
+from .efficientnet import EfficientNet, fold_conv_bn_nchw, params_stamp
 
 _H_MAX = 2.0      # DPhysConfig().h_max, the default range of ScaledTanh (lss.py:15-19)
 
@@ -135,17 +136,9 @@ class CamEncode(nn.Module):
         """Inference path: (BN, fH, fW, D + C) fp32 rows for the lift-splat kernel; `up1` and `depthnet` on tcgen05."""
         t = self.trunk
         # the trunk's depthwise / squeeze-excite / strided layers are memory-bound, not GEMM-shaped: they stay on
-        # cuDNN, but in bf16 channels-last so every activation pass moves half the bytes
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            x = x.contiguous(memory_format=torch.channels_last)
-            x = t._swish(t._bn0(t._conv_stem(x)))
-            feats, prev = [], x
-            for block in t._blocks:
-                x = block(x)
-                if prev.size(2) > x.size(2):
-                    feats.append(prev)
-                prev = x
-            feats.append(x)
+        # cuDNN, in bf16 channels-last (half the bytes per activation pass) with every BatchNorm folded into its
+        # convolution and one fused SiLU per activation (no separate BN / sigmoid / mul / pad passes)
+        feats = t.fast_endpoints(x)
         y = self.up1.fast_nhwc(feats[4].float(), feats[3].float())           # (BN, fH, fW, 512) bf16
         f = _folded(self, lambda: _fold_padded_cout(self.depthnet))
         logits = ops.conv_bn_act_nhwc(y, *f, ops.ACT_NONE)                    # (BN, fH, fW, 128) bf16, 123 used
@@ -200,11 +193,35 @@ class BevEncode(nn.Module):
         geom, diff, friction = self.up_geom(x), self.up_diff(x), self.up_friction(x)
         return {'geom': geom, 'terrain': geom - diff, 'diff': diff, 'friction': friction}
 
+    def fast_backbone_endpoints(self, x, dtype=torch.bfloat16):
+        """Eval-mode ResNet-18 stem + layer1..3 (lss.py:104-116) with every BatchNorm folded into its convolution, in
+        `dtype` channels-last: returns (layer1 output, layer3 output)."""
+        stamp = params_stamp(self)
+        cache = self.__dict__.get("_mfb_resnet_folded")
+        if cache is None or cache["stamp"] != stamp or cache["dtype"] != dtype:
+            with torch.no_grad():
+                layers = []
+                for layer in (self.layer1, self.layer2, self.layer3):
+                    for blk in layer:
+                        ds = fold_conv_bn_nchw(blk.downsample[0], blk.downsample[1], dtype) if blk.downsample is not None else None
+                        layers.append((blk, fold_conv_bn_nchw(blk.conv1, blk.bn1, dtype), fold_conv_bn_nchw(blk.conv2, blk.bn2, dtype), ds))
+                cache = {"stamp": stamp, "dtype": dtype, "stem": fold_conv_bn_nchw(self.conv1, self.bn1, dtype), "layers": layers}
+            self.__dict__["_mfb_resnet_folded"] = cache
+        conv = lambda t, c, wb: F.conv2d(t, wb[0], wb[1], c.stride, c.padding, c.dilation, c.groups)
+        x = x.to(dtype).contiguous(memory_format=torch.channels_last)
+        x = F.relu(conv(x, self.conv1, cache["stem"]))
+        x1 = None
+        n1 = len(self.layer1)
+        for i, (blk, f1, f2, ds) in enumerate(cache["layers"]):
+            idt = x if ds is None else conv(x, blk.downsample[0], ds)
+            x = F.relu(conv(F.relu(conv(x, blk.conv1, f1)), blk.conv2, f2).add_(idt))
+            if i == n1 - 1:
+                x1 = x
+        return x1, x
+
     def fast_forward(self, x):
         """Inference path: `up1` and the three head convs (one fused 256 -> 3x128 launch) on tcgen05."""
-        with torch.autocast("cuda", dtype=torch.bfloat16):                   # strided ResNet layers: cuDNN bf16 channels-last
-            x1 = self.layer1(self.relu(self.bn1(self.conv1(x.contiguous(memory_format=torch.channels_last)))))
-            x3 = self.layer3(self.layer2(x1))
+        x1, x3 = self.fast_backbone_endpoints(x)                             # strided ResNet layers: cuDNN bf16 channels-last
         y = self.up1.fast_nhwc(x3.float(), x1.float())                        # (B, X/2, Y/2, 256) bf16
         heads = (self.up_geom, self.up_diff, self.up_friction)
 

@@ -84,3 +84,45 @@ def test_network_restatement_matches_reference_golden_up_to_the_fused_stage():
     for k in ("geom", "terrain", "diff", "friction"):
         assert np.allclose(out[k].numpy(), g[k], rtol=1e-4, atol=1e-5), k
     assert vox.dtype == torch.int32 and int((vox >= 0).sum()) > 0 and int(vox.max()) < 64 * 64
+
+
+def test_folded_inference_weights_match_module_path():
+    """Host logic of the eval fast path: BatchNorm folded into the convolutions (EfficientNet trunk, ResNet-18 BEV
+    backbone) + fused SiLU must reproduce the module path in fp32, and an in-place weight update must drop the fold."""
+    import torch
+    from helpers_lss import small_cfg
+    from monoforce_b200 import LiftSplatShoot
+    torch.manual_seed(0)
+    gc, ac = small_cfg()
+    net = LiftSplatShoot(gc, ac).eval()
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.5); m.running_var.uniform_(0.5, 2.0)
+            m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.3)
+    rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
+    t = net.camencode.trunk
+    x = torch.randn(2, 3, 96, 128)
+    with torch.no_grad():
+        y = t._swish(t._bn0(t._conv_stem(x)))
+        feats, prev = [], y
+        for blk in t._blocks:
+            y = blk(y)
+            if prev.size(2) > y.size(2):
+                feats.append(prev)
+            prev = y
+        feats.append(y)
+        fast = t.fast_endpoints(x, dtype=torch.float32)
+        assert len(fast) == len(feats) == 5
+        for a, b in zip(fast, feats):
+            assert a.shape == b.shape and rel(a, b) < 1e-5
+        be = net.bevencode
+        xb = torch.randn(2, be.conv1.in_channels, 64, 64)
+        x1 = be.layer1(be.relu(be.bn1(be.conv1(xb)))); x3 = be.layer3(be.layer2(x1))
+        f1, f3 = be.fast_backbone_endpoints(xb, dtype=torch.float32)
+        assert rel(f1, x1) < 1e-5 and rel(f3, x3) < 1e-5
+        be.conv1.weight.mul_(1.1); t._conv_stem.weight.mul_(0.9)           # e.g. an optimizer step / load_state_dict
+        x1 = be.layer1(be.relu(be.bn1(be.conv1(xb))))
+        assert rel(be.fast_backbone_endpoints(xb, dtype=torch.float32)[0], x1) < 1e-5
+        y0 = t._swish(t._bn0(t._conv_stem(x)))
+        f0 = torch.nn.functional.silu(torch.nn.functional.conv2d(torch.nn.functional.pad(x, (0, 1, 0, 1)), *t.folded(torch.float32)["stem"], 2))
+        assert rel(f0, y0) < 1e-5
