@@ -68,12 +68,29 @@ class Up(nn.Module):
         return self.conv(torch.cat([x2, self.up(x1)], dim=1))
 
     def fast_nhwc(self, x1, x2):
-        """Inference path: NCHW fp32 in, NHWC bf16 out, both conv-BN-GELU triples on the tensor cores."""
-        x = torch.cat([x2, self.up(x1)], dim=1)
+        """Inference path: NCHW in (any float dtype; bf16 channels-last inputs are used as they are), NHWC bf16 out, both
+        conv-BN-GELU triples on the tensor cores."""
         f = _folded(self, lambda: [ops.fold_conv_bn(self.conv[0], self.conv[1]), ops.fold_conv_bn(self.conv[3], self.conv[4])])
-        x = _to_nhwc_bf16(x, f[0][0].shape[-1])
+        x = _cat_up_nhwc_bf16(self.up, x1, x2, f[0][0].shape[-1])
         x = ops.conv_bn_act_nhwc(x, *f[0], ops.ACT_GELU)
         return ops.conv_bn_act_nhwc(x, *f[1], ops.ACT_GELU)
+
+
+def _cat_up_nhwc_bf16(up, x1, x2, c_padded):
+    """cat([x2, up(x1)], channel) written straight into one (N,H,W,c_padded) bf16 buffer: the up-sampling runs in bf16
+    channels-last and the concatenation / layout change / zero padding are two strided copies, instead of the fp32
+    up-sample + cat + convert passes."""
+    x1 = x1.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    u = up(x1)
+    N, C2, H, W = x2.shape
+    C1 = u.shape[1]
+    assert u.shape[2:] == x2.shape[2:] and C1 + C2 <= c_padded
+    out = torch.empty(N, H, W, c_padded, dtype=torch.bfloat16, device=x2.device)
+    out[..., :C2] = x2.permute(0, 2, 3, 1)
+    out[..., C2:C2 + C1] = u.permute(0, 2, 3, 1)
+    if C1 + C2 < c_padded:
+        out[..., C1 + C2:] = 0
+    return out
 
 
 def _to_nhwc_bf16(x, c_padded):
@@ -139,7 +156,7 @@ class CamEncode(nn.Module):
         # cuDNN, in bf16 channels-last (half the bytes per activation pass) with every BatchNorm folded into its
         # convolution and one fused SiLU per activation (no separate BN / sigmoid / mul / pad passes)
         feats = t.fast_endpoints(x)
-        y = self.up1.fast_nhwc(feats[4].float(), feats[3].float())           # (BN, fH, fW, 512) bf16
+        y = self.up1.fast_nhwc(feats[4], feats[3])                           # (BN, fH, fW, 512) bf16
         f = _folded(self, lambda: _fold_padded_cout(self.depthnet))
         logits = ops.conv_bn_act_nhwc(y, *f, ops.ACT_NONE)                    # (BN, fH, fW, 128) bf16, 123 used
         return logits[..., :self.D + self.C].float().contiguous()
@@ -222,14 +239,14 @@ class BevEncode(nn.Module):
     def fast_forward(self, x):
         """Inference path: `up1` and the three head convs (one fused 256 -> 3x128 launch) on tcgen05."""
         x1, x3 = self.fast_backbone_endpoints(x)                             # strided ResNet layers: cuDNN bf16 channels-last
-        y = self.up1.fast_nhwc(x3.float(), x1.float())                        # (B, X/2, Y/2, 256) bf16
+        y = self.up1.fast_nhwc(x3, x1)                                        # (B, X/2, Y/2, 256) bf16
         heads = (self.up_geom, self.up_diff, self.up_friction)
 
         def build():
             parts = [ops.fold_conv_bn(h[1], h[2]) for h in heads]
             return [torch.cat([p[i] for p in parts]).contiguous() for i in range(3)]
         f = _folded(self, build)
-        up = heads[0][0](y.permute(0, 3, 1, 2).float())                       # shared x2 bilinear up-sampling
+        up = heads[0][0](y.permute(0, 3, 1, 2))                               # shared x2 bilinear up-sampling, bf16 channels-last
         z = ops.conv_bn_act_nhwc(_to_nhwc_bf16(up, 256), *f, ops.ACT_GELU)    # (B, X, Y, 384)
         z = z.permute(0, 3, 1, 2).float()
         geom, diff, friction = (h[5](h[4](z[:, 128 * i:128 * (i + 1)])) for i, h in enumerate(heads))
