@@ -168,3 +168,21 @@ def test_two_process_cost_gather_and_grad_allreduce_gloo(n):
         assert p.exitcode == 0
     for rank, ok, idx, val, gsum in res:
         assert ok and idx == n - 1 and val == 0.5 and gsum == 3.0
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's algorithm on the host cores, no GPU) must print ONE JSON line with the
+    keys the driver reads; a non-zero rank under torchrun prints nothing and exits 0."""
+    import json
+    import subprocess
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "2"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "0"})
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config",
+                "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "1"})
+    assert other.returncode == 0 and other.stdout.strip() == ""
