@@ -147,8 +147,10 @@ def _worker(rank, world, port, n, q):
     gathered = gather_costs(mine, n)
     idx, val = best_trajectory(mine, n)
     g = torch.full((4, 4), float(rank + 1))
-    allreduce_map_grads(g, None)
-    q.put((rank, torch.equal(gathered, all_costs), idx, val, float(g[0, 0])))
+    g2 = torch.arange(3, dtype=torch.float32) * (rank + 1)                   # second map: both travel as one flat all-reduce
+    allreduce_map_grads(g, None, g2)
+    ok_g2 = torch.equal(g2, torch.arange(3, dtype=torch.float32) * 3) and g.shape == (4, 4) and bool((g == g[0, 0]).all())
+    q.put((rank, torch.equal(gathered, all_costs) and ok_g2, idx, val, float(g[0, 0])))
     dist.destroy_process_group()
 
 
