@@ -9,11 +9,15 @@ One "step" = one pass of the hot path over one batch of synthetic input: BASELIN
 (all outputs of the reference API materialised, incl. the two (B,T,N,3) force tensors, plus the
 fused per-trajectory cost), physics_loss against ground-truth poses, adjoint backward to
 d/dz_grid and d/dfriction (the fit_terrain.py training-loss path).  For N > 1 the trajectory batch
-is sharded (weak scaling, 4096 per GPU); the per-shard costs are all-gathered and the two map
-gradients all-reduced over NCCL inside the timed step.
+is sharded (weak scaling, 4096 per GPU); the per-shard costs are all-gathered (issued right after the
+forward, overlapping the adjoint) and the two map gradients all-reduced over NCCL inside the timed step.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference
-(oracle/, proven bit-identical to the reference's PyTorch-CPU DPhysics) on a bounded sample.
+Prints ONE JSON line (rank 0).  Besides the contract keys the line carries the other BASELINE configs as
+extra blocks: `forward_only` (config 2), `encoder_cfg4` + `cfg4_e2e` (config 4), `cfg5` (config 5, at --gpus 8),
+`strong_scaling` (N > 1), `reference_published` (the one timing the reference publishes), `odeint` (the callers'
+default integrator at config 2/3 size), `small_batch` latencies and `shooting_e2e`.
+`--impl reference` times the CPU restatement of the reference (oracle/, proven bit-identical to the
+reference's PyTorch-CPU DPhysics) on a bounded sample.
 """
 import argparse
 import json
@@ -34,6 +38,7 @@ UNIT = "trajectory-steps/s"
 T_STEPS = 400
 GRID_RES = 0.05           # 256 x 256 map
 N_POINTS_BYTES = {"marv": 5432, "tradr": 4280}   # algorithmic bytes per trajectory-step
+N_SM, SUBPARTS = 148, 4
 
 
 def synth_inputs(B, seed, device=None, pin=False):
@@ -101,14 +106,26 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def measured_hbm_peak():
+def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            d = json.load(open(p))
+            return {"hbm": float(d["hbm_gbs"]), "bf16": float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1427.0))),
+                    "src": "measured (MEASURED_PEAKS.json)"}
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return {"hbm": 6650.0, "bf16": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def _profile_json(name):
+    p = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return {}
+    return {}
 
 
 def cpu_reference_run(B, steps, warmup, fwd_only=False):
@@ -119,8 +136,10 @@ def cpu_reference_run(B, steps, warmup, fwd_only=False):
     torch.set_num_threads(os.cpu_count() or 1)
     d = synth_inputs(B, seed=0)
     spec = make_spec(d["cfg"])
-    with torch.no_grad():
-        gt, _ = O.rollout(spec, d["z_gt"].unsqueeze(0).expand(B, -1, -1), d["controls"])
+    gt = None
+    if not fwd_only:
+        with torch.no_grad():
+            gt, _ = O.rollout(spec, d["z_gt"].unsqueeze(0).expand(B, -1, -1), d["controls"])
     times = []
     for i in range(warmup + steps):
         z = d["z0"].clone().requires_grad_(not fwd_only)
@@ -162,6 +181,261 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# timing helpers
+# ---------------------------------------------------------------------------------------------------------------
+def _ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+def timed_ms(fn, steps, warmup=3, sync=None):
+    """CUDA events on the current (launching) stream around `steps` calls, after `warmup` untimed ones."""
+    sync = sync or torch.cuda.synchronize
+    for _ in range(warmup):
+        fn()
+    sync()
+    a, b = _ev(), _ev()
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    sync()
+    return a.elapsed_time(b) / steps
+
+
+def wall_ms(fn, steps, warmup=3):
+    """Host wall clock with a device synchronise inside every call: a latency, what a blocking caller sees."""
+    for _ in range(warmup):
+        fn()
+        torch.cuda.synchronize()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    return {"median_ms": ts[len(ts) // 2], "min_ms": ts[0], "max_ms": ts[-1]}
+
+
+def guarded(fn):
+    """Extra blocks never break the headline line."""
+    try:
+        return fn()
+    except Exception as e:      # noqa: BLE001
+        import traceback
+        return {"error": repr(e), "trace": traceback.format_exc(limit=3)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# extra blocks (rank 0, one GPU)
+# ---------------------------------------------------------------------------------------------------------------
+def block_reference_published(dev, steps):
+    """The ONE timing the reference publishes: examples/diff_physics.ipynb cells 2-7 (64 trajectories x T=600, marv,
+    128x128 map `repeat`ed per trajectory, default config => use_odeint=True, autograd enabled): 1.154-1.170 s per call."""
+    from monoforce_b200 import DPhysics, DPhysConfig, generate_controls
+    cfg = DPhysConfig(robot="marv")
+    cfg.grid_res, cfg.d_max, cfg.traj_sim_time, cfg.dt = 0.1, 6.4, 6.0, 0.01
+    n, T, dt = cfg.n_sim_trajs, cfg.traj_sim_time, cfg.dt
+    H = int(2 * cfg.d_max / cfg.grid_res)
+    xg, yg = torch.meshgrid(torch.linspace(-cfg.d_max, cfg.d_max, H), torch.linspace(-cfg.d_max, cfg.d_max, H), indexing="ij")
+    z = (1.0 * torch.exp(-1.0 * ((xg - 0) ** 2 + (yg - 4) ** 2)) + 4.0 * torch.exp(-5.0 * ((xg - 1) ** 2 + (yg + 2) ** 2)) +
+         2.0 * torch.exp(-3.0 * ((xg + 2) ** 2 + (yg + 4) ** 2))) / 3.0
+    z = z.repeat(n, 1, 1).to(dev)
+    torch.manual_seed(0)
+    cf, _ = generate_controls(n_trajs=n // 2, v_range=(cfg.vel_max / 2, cfg.vel_max), w_range=(-cfg.omega_max, cfg.omega_max),
+                              time_horizon=T, dt=dt)
+    cb, _ = generate_controls(n_trajs=n // 2, v_range=(-cfg.vel_max, -cfg.vel_max / 2), w_range=(-cfg.omega_max, cfg.omega_max),
+                              time_horizon=T, dt=dt)
+    controls = torch.cat([cf, cb], 0).to(dev)
+    sim = DPhysics(cfg, device=dev)
+
+    def call():
+        states, forces = sim(z_grid=z, controls=controls)
+        return torch.norm(forces[0], dim=-1).std(dim=-1).std(dim=-1)          # notebook cell 8
+    lat = wall_ms(call, max(steps, 5))
+    steps_total = n * int(T / dt)
+    return {"workload": "diff_physics.ipynb cells 2-8: 64 trajectories x T=600, marv, 128x128 map repeated per trajectory, "
+                        "use_odeint=True (default), autograd enabled, forces materialised + path cost",
+            "published_s_per_call": [1.154, 1.170], "published_hardware": "unspecified CUDA GPU (notebook output)",
+            "ms_per_call": lat["median_ms"], "min_ms": lat["min_ms"], "timing": "host wall clock incl. synchronize, median",
+            "trajectory_steps_per_s": steps_total / (lat["median_ms"] * 1e-3),
+            "speedup_vs_published": 1154.0 / lat["median_ms"]}
+
+
+def block_odeint(dev, steps, d, states_gt, ts):
+    """The callers' default integrator (dphys_config.py:153 use_odeint=True) at config 2/3 size."""
+    from monoforce_b200 import DPhysics
+    from monoforce_b200.losses import physics_loss
+    import copy
+    cfg = copy.copy(d["cfg"])
+    cfg.use_odeint = True
+    sim = DPhysics(cfg, device=dev)
+    controls = d["controls"].to(dev)
+    z = d["z0"].to(dev).unsqueeze(0).requires_grad_(True)
+    fr = d["fr0"].to(dev).unsqueeze(0).requires_grad_(True)
+    B = controls.shape[0]
+
+    def fwd():
+        with torch.no_grad():
+            sim(z, controls, friction=fr)
+
+    def train():
+        z.grad = None
+        fr.grad = None
+        st, _ = sim(z, controls, friction=fr)
+        physics_loss(st, states_gt, ts, ts, 0.9).backward()
+    f_ms = timed_ms(fwd, steps)
+    t_ms = timed_ms(train, steps)
+    return {"workload": "config 2/3 with use_odeint=True (torchdiffeq fixed-grid Euler semantics: forces are time integrals)",
+            "forward_ms": f_ms, "forward_value": B * T_STEPS / (f_ms * 1e-3),
+            "fwd_bwd_ms": t_ms, "fwd_bwd_value": B * T_STEPS / (t_ms * 1e-3), "unit": UNIT}
+
+
+def block_small_batch(dev, steps):
+    """The reference's real call sizes: ROS shooting (monoforce_node.py:75: 64 trajectories, T=500, 128x128 map repeated,
+    no_grad, default odeint) and a training batch (train.py:231-246: bsz distinct 32x32 maps, given initial state)."""
+    from monoforce_b200 import DPhysics, DPhysConfig, generate_controls
+    from monoforce_b200.losses import physics_loss
+    out = {}
+    cfg = DPhysConfig(robot="marv")                     # grid_res 0.1 -> 128x128, traj_sim_time 5.0, use_odeint True
+    sim = DPhysics(cfg, device=dev)
+    torch.manual_seed(1)
+    controls, _ = generate_controls(n_trajs=cfg.n_sim_trajs, time_horizon=cfg.traj_sim_time, dt=cfg.dt,
+                                    v_range=(-1, 1), w_range=(-2, 2))
+    controls = controls.to(dev)
+    xg, yg = cfg.x_grid, cfg.y_grid
+    z = (torch.exp(-(xg - 2) ** 2 / 4) * torch.exp(-yg ** 2 / 2)).repeat(cfg.n_sim_trajs, 1, 1).to(dev)
+
+    def shoot():
+        with torch.no_grad():
+            states, forces = sim(z_grid=z, controls=controls)
+            return torch.norm(forces[0], dim=-1).std(dim=-1).std(dim=-1).argmin()
+    lat = wall_ms(shoot, max(steps, 10))
+    out["ros_shooting_B64_T500_128x128_odeint"] = {**lat, "trajectory_steps_per_s": 64 * 500 / (lat["median_ms"] * 1e-3)}
+
+    cfg2 = DPhysConfig(robot="marv", grid_res=0.4)      # 32x32 maps
+    sim2 = DPhysics(cfg2, device=dev)
+    bsz, T = 16, int(cfg2.traj_sim_time / cfg2.dt)
+    g = torch.Generator().manual_seed(2)
+    terrain = (0.1 * torch.randn(bsz, 32, 32, generator=g)).to(dev).requires_grad_(True)
+    fric = (0.5 + 0.3 * torch.rand(bsz, 32, 32, generator=g)).to(dev).requires_grad_(True)
+    ctrl = torch.stack([torch.rand(bsz, generator=g) * 0.5 + 0.3, torch.rand(bsz, generator=g) - 0.5], -1)
+    ctrl = ctrl.unsqueeze(1).repeat(1, T, 1).to(dev)
+    ts = (torch.arange(T) * cfg2.dt)[None].to(dev)
+    x0 = torch.zeros(bsz, 3, device=dev)
+    st0 = lambda: (x0.clone(), torch.zeros_like(x0), torch.eye(3, device=dev).repeat(bsz, 1, 1), torch.zeros_like(x0))
+    with torch.no_grad():
+        gt, _ = sim2(z_grid=torch.zeros_like(terrain), controls=ctrl, state=st0())
+
+    def train():
+        terrain.grad = None
+        fric.grad = None
+        st, _ = sim2(z_grid=terrain, controls=ctrl, state=st0(), friction=fric)
+        physics_loss(st, gt, ts, ts).backward()
+    lat2 = wall_ms(train, max(steps, 10))
+    out["training_B16_T500_distinct_32x32_odeint_fwd_bwd"] = {**lat2, "trajectory_steps_per_s": bsz * T / (lat2["median_ms"] * 1e-3)}
+    out["note"] = "one warp per trajectory: 64 trajectories occupy 16 of 148 SMs; these are latencies, not throughputs"
+    return out
+
+
+def block_shooting_e2e(dev, steps, d):
+    """Forward-only end to end: pinned host controls in -> fused per-trajectory costs back on the host, config 2 size."""
+    from monoforce_b200 import DPhysics
+    sim = DPhysics(d["cfg"], device=dev)
+    sim.fused_cost, sim.return_forces = True, False
+    B = d["controls"].shape[0]
+    z = d["z_gt"].to(dev).unsqueeze(0)
+    h_cost = torch.empty(B).pin_memory()
+
+    def call():
+        with torch.no_grad():
+            c = d["controls"].to(dev, non_blocking=True)
+            sim(z, c)
+            h_cost.copy_(sim.last_cost, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return int(h_cost.argmin())
+    ms = timed_ms(call, steps)
+    return {"workload": "controls (host, pinned) -> rollout (states + fused cost, forces not materialised) -> costs on the host; "
+                        "4096 x 400, shared 256x256 map",
+            "ms_per_step": ms, "value": B * T_STEPS / (ms * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": d["controls"].numel() * 4, "d2h_bytes_per_step": B * 4}
+
+
+def _cfg4_confs():
+    from helpers_lss import default_cfg
+    gc, ac = default_cfg()
+    gc["xbound"] = [-6.4, 6.4, 0.05]
+    gc["ybound"] = [-6.4, 6.4, 0.05]
+    ac["final_dim"] = [512, 512]
+    return gc, ac
+
+
+def block_encoder(dev, steps, cfg4, peaks):
+    """TerrainEncoder forward (eval, bf16 tensor-core path), 16 scenes x 4 cameras; images start in pinned HOST memory
+    and their copy is inside the timed region."""
+    from helpers_lss import default_cfg, make_inputs
+    from monoforce_b200 import LiftSplatShoot, _lib
+    import warnings
+    gc, ac = _cfg4_confs() if cfg4 else default_cfg()
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = LiftSplatShoot(gc, ac).to(dev).eval()
+    net.fast_inference = True
+    host = [t.pin_memory() for t in make_inputs(gc, ac, 16, 0)]
+    calib = [t.to(dev) for t in host[1:]]
+
+    def call():
+        with torch.no_grad():
+            return net(host[0].to(dev, non_blocking=True), *calib)
+    n0 = _lib.kernel_launches()
+    call()
+    launches = _lib.kernel_launches() - n0
+    ms = timed_ms(call, max(steps // 2, 5))
+    gflop_scene = 230.9 if cfg4 else 65.7          # SURVEY.md 8(a) A14 [FlopCounterMode]
+    tf = 16 * gflop_scene / ms
+    res = {"workload": ("BASELINE config 4 encoder: 16 scenes x 4 cams 512x512 -> 256x256 BEV" if cfg4 else
+                        "lss_cfg.yaml: 16 scenes x 4 cams 256x416 -> 128x128 BEV") + ", eval, images copied from pinned host memory",
+           "ms": ms, "scenes_per_s": 16 / (ms * 1e-3), "h2d_bytes": host[0].numel() * 4, "repo_kernel_launches": int(launches),
+           "tflops": tf, "frac_of_sustained_bf16_peak": tf / peaks["bf16"], "peak_tflops": peaks["bf16"]}
+    return res, net, host, calib
+
+
+def block_cfg4_e2e(dev, steps, net, host, calib):
+    """BASELINE config 4 end to end: images (host) -> encoder -> terrain / friction maps -> 16 scenes x 256 control
+    sequences (one map per scene, map groups) -> fused costs -> host."""
+    from monoforce_b200 import DPhysics, DPhysConfig
+    cfg = DPhysConfig(robot="marv", grid_res=0.05)
+    cfg.traj_sim_time, cfg.use_odeint = T_STEPS * cfg.dt, False
+    sim = DPhysics(cfg, device=dev)
+    sim.fused_cost = True
+    per_scene, scenes = 256, 16
+    n = per_scene * scenes
+    g = torch.Generator().manual_seed(0)
+    ctrl = torch.stack([torch.rand(n, generator=g) * 0.5 + 0.5, torch.rand(n, generator=g) * 4 - 2], -1)
+    ctrl = ctrl.unsqueeze(1).repeat(1, T_STEPS, 1).contiguous().pin_memory()
+    h_cost = torch.empty(n).pin_memory()
+    parts = {}
+
+    def call(forces=True):
+        sim.return_forces = forces
+        with torch.no_grad():
+            out = net(host[0].to(dev, non_blocking=True), *calib)
+            c = ctrl.to(dev, non_blocking=True)
+            sim(out["terrain"].squeeze(1), c, friction=out["friction"].squeeze(1))      # (16,256,256) maps, 4096 trajectories
+            h_cost.copy_(sim.last_cost, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return h_cost.view(scenes, per_scene).argmin(dim=1)
+    ms = timed_ms(call, max(steps // 2, 5))
+    ms_nf = timed_ms(lambda: call(False), max(steps // 2, 5))
+    sim.return_forces = True
+    return {"workload": "images (host) -> LiftSplatShoot (eval) -> terrain/friction (16 x 256x256) -> DPhysics rollout, 16 scenes x "
+                        "256 trajectories x T=400 (one map per scene), all reference outputs materialised + fused cost -> costs on host",
+            "ms": ms, "scenes_per_s": scenes / (ms * 1e-3), "trajectory_steps_per_s": n * T_STEPS / (ms * 1e-3),
+            "ms_without_force_tensors": ms_nf, "h2d_bytes": host[0].numel() * 4 + ctrl.numel() * 4, "d2h_bytes": n * 4, **parts}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,6 +446,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=64, help="trajectories per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-encoder", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline + roofline + e2e only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -193,40 +468,57 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
-
-    B = args.traj_per_gpu
-    d = synth_inputs(B, seed=rank, pin=True)        # each rank owns a different shard of control sequences
-    cfg = d["cfg"]
-    N = cfg.robot_points.shape[0]
-    sim = DPhysics(cfg, device=dev)
-    sim.fused_cost = True
-    controls = d["controls"].to(dev)
-    ts = d["ts"].to(dev)
-    z_gt = d["z_gt"].to(dev).unsqueeze(0)
-    with torch.no_grad():
-        states_gt, _ = sim(z_gt, controls)
-        states_gt = tuple(s.clone() for s in states_gt)
-    z = d["z0"].to(dev).unsqueeze(0).requires_grad_(True)
-    fr = d["fr0"].to(dev).unsqueeze(0).requires_grad_(True)
-    costs_all = torch.empty(world * B, device=dev) if world > 1 else None
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def step(record=False):
-        z.grad = None
-        fr.grad = None
-        states, forces = sim(z, controls, friction=fr)
-        loss = physics_loss(states, states_gt, ts, ts, 0.9)
-        loss.backward()
-        if world > 1:
-            dist.all_gather_into_tensor(costs_all, sim.last_cost)
-            allreduce_map_grads(z.grad, fr.grad)           # both 256 KiB maps in one flat all-reduce
-        return loss
+    peaks = measured_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(*vals):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def make_job(B, seed):
+        """Config 3 on B trajectories of this rank: returns (step, sim, tensors)."""
+        d = synth_inputs(B, seed=seed, pin=True)
+        sim = DPhysics(d["cfg"], device=dev)
+        sim.fused_cost = True
+        controls = d["controls"].to(dev)
+        ts = d["ts"].to(dev)
+        z_gt = d["z_gt"].to(dev).unsqueeze(0)
+        with torch.no_grad():
+            states_gt, _ = sim(z_gt, controls)
+            states_gt = tuple(s.clone() for s in states_gt)
+        z = d["z0"].to(dev).unsqueeze(0).requires_grad_(True)
+        fr = d["fr0"].to(dev).unsqueeze(0).requires_grad_(True)
+        costs_all = torch.empty(world * B, device=dev)
+        # the kernel writes this rank's costs straight into its slice of the gather buffer (in-place all-gather)
+        sim.cost_buffer = costs_all[rank * B:(rank + 1) * B]
+
+        def step():
+            z.grad = None
+            fr.grad = None
+            states, forces = sim(z, controls, friction=fr)
+            work = None
+            if world > 1:     # depends on the forward only: travels while the adjoint runs
+                work = dist.all_gather_into_tensor(costs_all, sim.cost_buffer, async_op=True)
+            loss = physics_loss(states, states_gt, ts, ts, 0.9)
+            loss.backward()
+            if world > 1:
+                allreduce_map_grads(z.grad, fr.grad)           # both 256 KiB maps: one flat in-place all-reduce
+                work.wait()
+            return loss
+        return step, sim, dict(d=d, controls=controls, ts=ts, states_gt=states_gt, z=z, fr=fr, costs_all=costs_all)
+
+    B = args.traj_per_gpu
+    step, sim, J = make_job(B, seed=rank)        # each rank owns a different shard of control sequences
+    d, controls, ts, states_gt, z, fr, costs_all = (J[k] for k in ("d", "controls", "ts", "states_gt", "z", "fr", "costs_all"))
+    cfg = d["cfg"]
+    N = cfg.robot_points.shape[0]
 
     for _ in range(args.warmup):
         step()
@@ -235,60 +527,32 @@ def main():
     sampler.start()
     sim.timings = []          # CUDA events bracketing exactly the C-ABI calls on the launching stream
     n0 = _lib.kernel_launches()
-    t_a, t_b = ev(), ev()
+    t_a, t_b = _ev(), _ev()
     t_a.record()
     for _ in range(args.steps):
-        loss = step(record=True)
+        loss = step()
     t_b.record()
     barrier()
     launches = _lib.kernel_launches() - n0
     clocks = sampler.stop()
-    ms_total = t_a.elapsed_time(t_b)
-    ms_step = ms_total / args.steps
+    ms_step = t_a.elapsed_time(t_b) / args.steps
     fwd_t = [a.elapsed_time(b_) for n, a, b_ in sim.timings if n == "forward"]
     bwd_t = [a.elapsed_time(b_) for n, a, b_ in sim.timings if n == "backward"]
     sim.timings = None
     fwd_ms, bwd_ms = sum(fwd_t) / len(fwd_t), sum(bwd_t) / len(bwd_t)
-    if world > 1:
-        t = torch.tensor([ms_step, fwd_ms, bwd_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, fwd_ms, bwd_ms = t.tolist()
+    ms_step, fwd_ms, bwd_ms = max_over_ranks(ms_step, fwd_ms, bwd_ms)
     value = world * B * T_STEPS / (ms_step * 1e-3)
 
     # ---- forward-only (BASELINE config 2) ----
-    with torch.no_grad():
-        for _ in range(3):
+    def fwd_only():
+        with torch.no_grad():
             sim(z, controls, friction=fr)
-        torch.cuda.synchronize()
-        f_a, f_b = ev(), ev()
-        f_a.record()
-        for _ in range(args.steps):
-            sim(z, controls, friction=fr)
-        f_b.record()
-        torch.cuda.synchronize()
-    fwd_only_ms = f_a.elapsed_time(f_b) / args.steps
-    if world > 1:
-        t = torch.tensor([fwd_only_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        fwd_only_ms = t.item()
+    (fwd_only_ms,) = max_over_ranks(timed_ms(fwd_only, args.steps))
 
     # ---- training step that never materialises the two force tensors (reported separately, never as an HBM fraction) ----
     sim.return_forces = False
-    for _ in range(2):
-        step()
-    barrier()
-    n_a, n_b = ev(), ev()
-    n_a.record()
-    for _ in range(args.steps):
-        step()
-    n_b.record()
-    barrier()
+    (noforce_ms,) = max_over_ranks(timed_ms(step, args.steps, warmup=2, sync=barrier))
     sim.return_forces = True
-    noforce_ms = n_a.elapsed_time(n_b) / args.steps
-    if world > 1:
-        t = torch.tensor([noforce_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        noforce_ms = t.item()
 
     # ---- end to end through the public API with HOST inputs / outputs ----
     h_controls, h_z, h_fr = d["controls"], d["z0"], d["fr0"]
@@ -302,82 +566,103 @@ def main():
         z_dev = h_z.to(dev, non_blocking=True).unsqueeze(0).requires_grad_(True)
         f_dev = h_fr.to(dev, non_blocking=True).unsqueeze(0).requires_grad_(True)
         states, _ = sim(z_dev, c_dev, friction=f_dev)
+        work = dist.all_gather_into_tensor(costs_all, sim.cost_buffer, async_op=True) if world > 1 else None
         l = physics_loss(states, states_gt, ts, ts, 0.9)
         l.backward()
         if world > 1:
-            dist.all_gather_into_tensor(costs_all, sim.last_cost)
             allreduce_map_grads(z_dev.grad, f_dev.grad)
+            work.wait()
         h_gz.copy_(z_dev.grad[0], non_blocking=True)
         h_gfr.copy_(f_dev.grad[0], non_blocking=True)
         h_cost.copy_(sim.last_cost, non_blocking=True)
         h_loss.copy_(l.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the loss every step
         return float(h_loss)
-
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    e_a, e_b = ev(), ev()
-    e_a.record()
-    for _ in range(args.steps):
-        e2e_step()
-    e_b.record()
-    barrier()
-    e2e_ms = e_a.elapsed_time(e_b) / args.steps
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = t.item()
+    (e2e_ms,) = max_over_ranks(timed_ms(e2e_step, args.steps, sync=barrier))
     h2d = h_controls.numel() * 4 + h_z.numel() * 4 + h_fr.numel() * 4
     d2h = h_gz.numel() * 4 + h_gfr.numel() * 4 + h_cost.numel() * 4 + 4
 
-    peak, peak_src = measured_hbm_peak()
     bytes_per_launch = B * T_STEPS * N_POINTS_BYTES["marv"]
     achieved = bytes_per_launch / (fwd_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "fwd_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    traffic = _profile_json("fwd_traffic.json").get("dram_bytes_per_launch")
+    # adjoint: issue-bound (165 MB of DRAM traffic per launch).  Roofline = warp-instructions issued per second against one
+    # instruction per cycle per SM sub-partition; instructions per trajectory-step from the committed ncu capture.
+    bwd_prof = _profile_json("bwd_inst.json")
+    roofline_bwd = None
+    if bwd_prof.get("warp_inst_per_traj_step"):
+        clk = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965) * 1e6
+        inst = float(bwd_prof["warp_inst_per_traj_step"]) * B * T_STEPS
+        ach = inst / (bwd_ms * 1e-3)
+        pk = N_SM * SUBPARTS * clk
+        roofline_bwd = {"bound": "issue", "kernel": bwd_prof.get("kernel", "rollout_bwd_sweep_kernel<float,step>"),
+                        "achieved": ach / 1e9, "peak": pk / 1e9, "unit": "Gwarp-inst/s", "frac": ach / pk,
+                        "warp_inst_per_traj_step": bwd_prof["warp_inst_per_traj_step"], "kernel_ms": bwd_ms,
+                        "sm_mhz": clk / 1e6, "source": bwd_prof.get("source"),
+                        "dram_bytes_per_launch": bwd_prof.get("dram_bytes_per_launch")}
 
-    # ---- BASELINE config 4 in brief: terrain encoder (16 scenes x 4 cameras, lss_cfg.yaml sizes, eval fast path) ----
-    encoder = None
-    if rank == 0 and world == 1 and not args.no_encoder:
-        try:
-            from helpers_lss import default_cfg, make_inputs
-            from monoforce_b200 import LiftSplatShoot
-            gc, ac = default_cfg()
-            torch.manual_seed(0)
-            net = LiftSplatShoot(gc, ac).to(dev).eval()
-            net.fast_inference = True
-            enc_in = [t.to(dev) for t in make_inputs(gc, ac, 16, 0)]
-            with torch.no_grad():
-                for _ in range(3):
-                    net(*enc_in)
-                torch.cuda.synchronize()
-                g_a, g_b = ev(), ev()
-                g_a.record()
-                for _ in range(5):
-                    net(*enc_in)
-                g_b.record()
-                torch.cuda.synchronize()
-            enc_ms = g_a.elapsed_time(g_b) / 5
-            encoder = {"workload": "LiftSplatShoot forward, 16 scenes x 4 cams 256x416 -> 128x128 BEV, eval, "
-                                   "tcgen05 dense layers + fused lift-splat", "ms": enc_ms, "scenes_per_s": 16 / (enc_ms * 1e-3)}
-            del net, enc_in
-        except Exception as e:     # the encoder is an extra; never let it break the headline line
-            encoder = {"error": repr(e)}
+    # ---- multi-GPU extras: strong scaling of config 3 (4096 trajectories in total) and BASELINE config 5 ----
+    strong = cfg5 = None
+    if world > 1:
+        Bs = 4096 // world
+        s_step, s_sim, _ = make_job(Bs, seed=100 + rank)
+        (s_ms,) = max_over_ranks(timed_ms(s_step, args.steps, sync=barrier))
+        strong = {"workload": f"config 3 with 4096 trajectories IN TOTAL ({Bs} per GPU), same collectives", "ms_per_step": s_ms,
+                  "value": 4096 * T_STEPS / (s_ms * 1e-3), "unit": UNIT, "scaling": "strong"}
+        del s_step, s_sim
+        if world == 8:
+            B5 = 8192
+            c_step, c_sim, C5 = make_job(B5, seed=200 + rank)
+
+            def shoot5():
+                with torch.no_grad():
+                    c_sim(C5["z"], C5["controls"], friction=C5["fr"])
+                    dist.all_gather_into_tensor(C5["costs_all"], c_sim.cost_buffer)
+                    return C5["costs_all"].argmin()
+            (f5,) = max_over_ranks(timed_ms(shoot5, args.steps, sync=barrier))
+            (t5,) = max_over_ranks(timed_ms(c_step, max(args.steps // 2, 3), sync=barrier))
+            cfg5 = {"workload": "BASELINE config 5: 65536 trajectories x T=400 over 8 GPUs (8192 per GPU), all reference outputs "
+                                "materialised, NCCL all-gather of the per-shard costs inside the timed step",
+                    "forward_allgather_ms": f5, "forward_value": 8 * B5 * T_STEPS / (f5 * 1e-3),
+                    "fwd_bwd_ms": t5, "fwd_bwd_value": 8 * B5 * T_STEPS / (t5 * 1e-3), "unit": UNIT}
+            del c_step, c_sim, C5
+        torch.cuda.empty_cache()
+
+    extras = {}
+    solo = rank == 0 and world == 1
+    if solo and not args.no_extras:
+        extras["reference_published"] = guarded(lambda: block_reference_published(dev, args.steps))
+        extras["odeint"] = guarded(lambda: block_odeint(dev, args.steps, d, states_gt, ts))
+        extras["small_batch"] = guarded(lambda: block_small_batch(dev, args.steps))
+        extras["shooting_e2e"] = guarded(lambda: block_shooting_e2e(dev, args.steps, d))
+    # ---- BASELINE config 4: terrain encoder alone (default + config-4 sizes) and encoder -> rollout end to end ----
+    if solo and not args.no_encoder:
+        del states_gt
+        torch.cuda.empty_cache()
+
+        def enc_blocks():
+            res, net, host, calib = block_encoder(dev, args.steps, False, peaks)
+            extras["encoder"] = res
+            del net, host, calib
+            res4, net4, host4, calib4 = block_encoder(dev, args.steps, True, peaks)
+            extras["encoder_cfg4"] = res4
+            extras["cfg4_e2e"] = guarded(lambda: block_cfg4_e2e(dev, args.steps, net4, host4, calib4))
+            return True
+        r = guarded(enc_blocks)
+        if r is not True:
+            extras.setdefault("encoder", r)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if solo and not args.no_cpu_baseline:
         Bc = args.cpu_sample
         sec = cpu_reference_run(Bc, steps=1, warmup=1)
         cores = os.cpu_count() or 1
         cpu = {"value": Bc * T_STEPS / sec, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{Bc} trajectories x {T_STEPS} steps fwd+bwd (same map/controls recipe), 1 warm-up + 1 timed pass, "
                          f"torch-CPU oracle with {cores} threads"}
+        if not args.no_extras:
+            sec_f = cpu_reference_run(256, steps=1, warmup=0, fwd_only=True)
+            cpu["forward_no_grad"] = {"value": 256 * T_STEPS / sec_f, "unit": UNIT,
+                                      "sample": "256 trajectories x 400 steps forward under no_grad, 1 timed pass (BASELINE.md section 4)"}
 
     if rank == 0:
         line = {
@@ -389,10 +674,12 @@ def main():
                        "robot": "marv", "n_points": N, "map": "256x256 shared (grid_res 0.05)", "T": T_STEPS,
                        "trajectories_per_gpu": B, "global_trajectories": world * B,
                        "l2": "each step writes 8.9 GB of outputs >> 126 MB L2 (inputs 13.6 MB), so no explicit flush",
-                       "collectives": "none" if world == 1 else "all_gather(costs) + one flat all_reduce(grad z | grad friction) per step"},
+                       "collectives": "none" if world == 1 else "all_gather(costs), issued after the forward and overlapped with the "
+                                      "adjoint + one flat in-place all_reduce(grad z | grad friction) per step"},
             "roofline": {"bound": "hbm", "kernel": "rollout_fwd_kernel<float,7,step,forces,cost>", "achieved": achieved,
-                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                         "peak": peaks["hbm"], "peak_source": peaks["src"], "unit": "GB/s", "frac": achieved / peaks["hbm"],
                          "algorithmic_bytes_per_launch": bytes_per_launch, "kernel_ms": fwd_ms, "traffic": traffic},
+            "roofline_bwd": roofline_bwd,
             "kernels_ms": {"forward_call (cell table + rollout_fwd)": fwd_ms,
                            "backward_call (cell table + rollout_bwd + grad scatter)": bwd_ms},
             "forward_only": {"value": world * B * T_STEPS / (fwd_only_ms * 1e-3), "unit": UNIT, "ms_per_step": fwd_only_ms,
@@ -406,7 +693,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "cpu_baseline": cpu,
-            "encoder": encoder,
+            "strong_scaling": strong,
+            "cfg5": cfg5,
+            **extras,
             "loss": float(loss.detach()),
         }
         print(json.dumps(line), flush=True)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MFB_ABI_VERSION 2
+#define MFB_ABI_VERSION 3
 
 typedef enum mfb_status {
     MFB_OK = 0,
@@ -49,8 +49,10 @@ typedef struct mfb_rollout_desc {
     int32_t H, W;         /* height-map size; the reference requires H == W           */
     int32_t n_tracks;     /* 2 or 4 driving parts (dphysics.py:75-104)                */
     int32_t variant;      /* mfb_variant                                              */
-    int32_t reserved;
-    int64_t map_stride;   /* elements between consecutive trajectories' maps; 0 = all trajectories share one map */
+    int32_t traj_per_map; /* with map_stride != 0: consecutive trajectories that read the same map (trajectory b uses map
+                             b / traj_per_map: one map per scene, many control sequences per scene - the shooting call of
+                             monoforce_ros/nodes/monoforce_node.py:75,156 batched over scenes); 0 or 1 = one map per trajectory */
+    int64_t map_stride;   /* elements between consecutive maps; 0 = all trajectories share one map */
     double mass, gravity, stiffness, damping, grid_res, d_max, dt, omega_max;
     double robot_Ly;      /* robot_size[1] (track gauge), dphys_config.py:43          */
     double I_inv[9];      /* inverse of the body-frame inertia tensor, row-major (dphysics.py:152-153) */
@@ -60,8 +62,8 @@ typedef struct mfb_rollout_desc {
 /* Inputs and outputs of the forward rollout.  Shapes follow DPhysics.forward. */
 typedef struct mfb_rollout_buffers {
     /* inputs */
-    const void* z_grid;     /* (B or 1, H, W) height map(s)                           */
-    const void* friction;   /* (B or 1, H, W) friction map(s)                         */
+    const void* z_grid;     /* (n_maps, H, W) height map(s), n_maps = 1, B or ceil(B / traj_per_map) */
+    const void* friction;   /* (n_maps, H, W) friction map(s)                         */
     const void* controls;   /* (B, T, 2) (v, w) per step                              */
     const void* x0;         /* (B, 3)   initial position  (z component is overwritten by the start-height snap, see x0z) */
     const void* xd0;        /* (B, 3)   initial velocity                              */
@@ -103,8 +105,8 @@ typedef struct mfb_rollout_grads {
     const void* g_F_frictions;/* (B, T, N, 3) */
     const void* g_x0z;        /* (B,) gradient w.r.t. the snapped start height output */
     /* outgoing: d loss / d input.  Map gradients are ACCUMULATED (+=) into zero-initialised buffers. */
-    void* g_z_grid;           /* (B or 1, H, W) */
-    void* g_friction;         /* (B or 1, H, W) */
+    void* g_z_grid;           /* (n_maps, H, W) */
+    void* g_friction;         /* (n_maps, H, W) */
     void* g_controls;         /* (B, T, 2)      */
     void* g_x0;               /* (B, 3)  (z component is always 0: the snap overwrites it) */
     void* g_xd0;              /* (B, 3)         */

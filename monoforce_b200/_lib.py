@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
 class RolloutDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("T", C.c_int32), ("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-        ("n_tracks", C.c_int32), ("variant", C.c_int32), ("reserved", C.c_int32),
+        ("n_tracks", C.c_int32), ("variant", C.c_int32), ("traj_per_map", C.c_int32),
         ("map_stride", C.c_int64),
         ("mass", C.c_double), ("gravity", C.c_double), ("stiffness", C.c_double), ("damping", C.c_double),
         ("grid_res", C.c_double), ("d_max", C.c_double), ("dt", C.c_double), ("omega_max", C.c_double),

@@ -37,8 +37,19 @@ static const char* check_desc(const mfb_rollout_desc* d) {
     if (d->n_tracks != 2 && d->n_tracks != 4) return "n_tracks must be 2 or 4";
     if (d->variant != MFB_STEP_LOOP && d->variant != MFB_ODEINT_EULER) return "unknown variant";
     if (d->map_stride != 0 && d->map_stride < (long long)d->H * d->W) return "map_stride must be 0 or >= H*W";
+    if (d->traj_per_map < 0) return "traj_per_map must be >= 0";
     if (!(d->grid_res > 0) || !(d->dt > 0) || !(d->mass > 0)) return "grid_res, dt and mass must be positive";
     return nullptr;
+}
+
+// trajectories per map: 0 keeps the ABI-v2 meaning (map_stride == 0: all share one map, else one map per trajectory)
+static int map_group(const mfb_rollout_desc& d) {
+    if (d.map_stride == 0) return d.B;
+    return d.traj_per_map > 0 ? d.traj_per_map : 1;
+}
+static long long map_count(const mfb_rollout_desc& d) {
+    const int g = map_group(d);
+    return ((long long)d.B + g - 1) / g;
 }
 
 template <typename T>
@@ -46,6 +57,7 @@ static RolloutArgs<T> make_args(const mfb_rollout_desc& d, const mfb_rollout_buf
     RolloutArgs<T> a;
     a.B = d.B; a.nT = d.T; a.N = d.N; a.H = d.H; a.W = d.W; a.n_tracks = d.n_tracks;
     a.map_stride = d.map_stride;
+    a.map_group = map_group(d);
     a.mass = (T)d.mass;
     a.inv_mass = (T)1 / (T)d.mass;
     a.mg = (T)(d.mass * d.gravity);                         // clamp bounds / gravity force: python double product, then cast
@@ -86,12 +98,12 @@ static const char* check_io_forward(const mfb_rollout_desc& d, const mfb_rollout
 
 // workspace layout: [cell table: n_maps*H*W*12 scalars][map-gradient scratch: n_maps*H*W*8 scalars]
 static long long table_elems(const mfb_rollout_desc& d) {
-    const long long n_maps = d.map_stride == 0 ? 1 : d.B;
+    const long long n_maps = map_count(d);
     return n_maps * d.H * d.W * kCellStride;
 }
 constexpr int kGradScratchPerCell = 8;   // per-cell corner records of the single-sweep adjoint (the three-pass kernel uses 2)
 static long long workspace_bytes(const mfb_rollout_desc& d, int dtype) {
-    const long long n_maps = d.map_stride == 0 ? 1 : d.B;
+    const long long n_maps = map_count(d);
     return (table_elems(d) + n_maps * d.H * d.W * kGradScratchPerCell) * (dtype == MFB_F32 ? 4 : 8);
 }
 
@@ -105,7 +117,7 @@ static const char* check_workspace(const mfb_rollout_desc& d, const mfb_rollout_
 // K0: packed per-cell sampling table (one thread per cell), rebuilt on every call
 template <typename T>
 static int build_table(const mfb_rollout_desc& d, const mfb_rollout_buffers& io, cudaStream_t st) {
-    const int n_maps = d.map_stride == 0 ? 1 : d.B;
+    const int n_maps = (int)map_count(d);
     const long long total = (long long)n_maps * d.H * d.W;
     const int block = 256;
     const int grid = (int)std::min<long long>((total + block - 1) / block, 148 * 32);
@@ -137,7 +149,7 @@ static int backward_typed(const mfb_rollout_desc& d, const mfb_rollout_buffers& 
     AdjointArgs<T> ga;
     ga.g_Xs = (const T*)g.g_Xs; ga.g_Xds = (const T*)g.g_Xds; ga.g_Rs = (const T*)g.g_Rs; ga.g_Oms = (const T*)g.g_Omegas;
     ga.g_Fs = (const T*)g.g_F_springs; ga.g_Ff = (const T*)g.g_F_frictions; ga.g_x0z = (const T*)g.g_x0z;
-    const long long n_maps = d.map_stride == 0 ? 1 : d.B;
+    const long long n_maps = map_count(d);
     const bool want_maps = g.g_z_grid || g.g_friction;
     if (want_maps && d.map_stride != 0 && d.map_stride != (long long)d.H * d.W)
         return fail(MFB_ERR_UNSUPPORTED, "map gradients need densely packed per-trajectory maps (map_stride == H*W)");
@@ -216,17 +228,17 @@ int mfb_rollout_forward_host(const mfb_rollout_desc* desc, const mfb_rollout_buf
     const mfb_rollout_desc& d = *desc;
     const size_t es = dtype == MFB_F32 ? 4 : 8;
     const size_t B = d.B, T = d.T, N = d.N, HW = (size_t)d.H * d.W;
-    const size_t n_maps = d.map_stride == 0 ? 1 : B;
-    const size_t map_elems = d.map_stride == 0 ? HW : (size_t)d.map_stride * (B - 1) + HW;
+    const size_t n_maps = (size_t)map_count(d);
+    const size_t map_elems = (size_t)d.map_stride * (n_maps - 1) + HW;
 
     // layout of the scratch arena
     struct Seg { size_t off, bytes; };
     size_t cur = 0;
     auto seg = [&](size_t bytes) { Seg s{cur, bytes}; cur += align_up(bytes); return s; };
-    (void)n_maps;
     Seg s_z = seg(map_elems * es), s_mu = seg(map_elems * es), s_ctrl = seg(B * T * 2 * es);
     Seg s_x0 = seg(B * 3 * es), s_xd0 = seg(B * 3 * es), s_R0 = seg(B * 9 * es), s_om0 = seg(B * 3 * es);
     Seg s_pts = seg(N * 3 * es), s_part = seg(N * 4), s_ts = seg(T * es);
+    Seg s_ja = seg(io->joint_angles ? B * T * 4 * es : 0);
     Seg s_Xs = seg(B * T * 3 * es), s_Xds = seg(B * T * 3 * es), s_Rs = seg(B * T * 9 * es), s_Oms = seg(B * T * 3 * es);
     Seg s_x0z = seg(B * es), s_cost = seg(B * es);
     const bool forces = io->F_springs != nullptr;
@@ -237,12 +249,24 @@ int mfb_rollout_forward_host(const mfb_rollout_desc* desc, const mfb_rollout_buf
     cudaError_t ce = cudaSetDevice(device);
     if (ce != cudaSuccess) return fail(MFB_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
     if (g_scratch.device != device || g_scratch.cap < cur) {
+        // the arena and its stream belong to ONE device: release them under that device before moving on
+        if (g_scratch.device >= 0 && g_scratch.device != device) {
+            cudaSetDevice(g_scratch.device);
+            if (g_scratch.stream) cudaStreamDestroy(g_scratch.stream);
+            g_scratch.stream = nullptr;
+            if (g_scratch.ptr) cudaFree(g_scratch.ptr);
+            g_scratch.ptr = nullptr; g_scratch.cap = 0;
+            cudaSetDevice(device);
+        }
         if (g_scratch.ptr) cudaFree(g_scratch.ptr);
-        g_scratch.ptr = nullptr; g_scratch.cap = 0;
+        g_scratch.ptr = nullptr; g_scratch.cap = 0; g_scratch.device = -1;
         ce = cudaMalloc(&g_scratch.ptr, cur);
         if (ce != cudaSuccess) return fail(MFB_ERR_CUDA, std::string("cudaMalloc scratch: ") + cudaGetErrorString(ce));
         g_scratch.cap = cur; g_scratch.device = device;
-        if (!g_scratch.stream) cudaStreamCreateWithFlags(&g_scratch.stream, cudaStreamNonBlocking);
+        if (!g_scratch.stream) {
+            ce = cudaStreamCreateWithFlags(&g_scratch.stream, cudaStreamNonBlocking);
+            if (ce != cudaSuccess) return fail(MFB_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(ce));
+        }
     }
     char* base = (char*)g_scratch.ptr;
     cudaStream_t st = g_scratch.stream;
@@ -250,13 +274,14 @@ int mfb_rollout_forward_host(const mfb_rollout_desc* desc, const mfb_rollout_buf
     auto d2h = [&](void* dst, Seg s) { if (dst && s.bytes) cudaMemcpyAsync(dst, base + s.off, s.bytes, cudaMemcpyDeviceToHost, st); };
     h2d(s_z, io->z_grid); h2d(s_mu, io->friction); h2d(s_ctrl, io->controls);
     h2d(s_x0, io->x0); h2d(s_xd0, io->xd0); h2d(s_R0, io->R0); h2d(s_om0, io->omega0);
-    h2d(s_pts, io->points); h2d(s_part, io->part_id); h2d(s_ts, io->ts);
+    h2d(s_pts, io->points); h2d(s_part, io->part_id); h2d(s_ts, io->ts); h2d(s_ja, io->joint_angles);
 
     mfb_rollout_buffers dev = *io;
     dev.z_grid = base + s_z.off; dev.friction = base + s_mu.off; dev.controls = base + s_ctrl.off;
     dev.x0 = base + s_x0.off; dev.xd0 = base + s_xd0.off; dev.R0 = base + s_R0.off; dev.omega0 = base + s_om0.off;
     dev.points = base + s_pts.off; dev.part_id = (const int32_t*)(base + s_part.off);
     dev.ts = io->ts ? base + s_ts.off : nullptr;
+    dev.joint_angles = io->joint_angles ? base + s_ja.off : nullptr;   // (B,T,4) host -> device like every other input
     dev.Xs = base + s_Xs.off; dev.Xds = base + s_Xds.off; dev.Rs = base + s_Rs.off; dev.Omegas = base + s_Oms.off;
     dev.x0z = base + s_x0z.off;
     dev.cost = io->cost ? base + s_cost.off : nullptr;
@@ -287,6 +312,9 @@ long long mfb_kernel_launches(void) { return g_launches.load(); }
 
 void mfb_release_scratch(void) {
     std::lock_guard<std::mutex> lock(g_scratch.mu);
+    if (g_scratch.device >= 0) cudaSetDevice(g_scratch.device);
+    if (g_scratch.stream) cudaStreamDestroy(g_scratch.stream);
+    g_scratch.stream = nullptr;
     if (g_scratch.ptr) cudaFree(g_scratch.ptr);
     g_scratch.ptr = nullptr; g_scratch.cap = 0; g_scratch.device = -1;
 }

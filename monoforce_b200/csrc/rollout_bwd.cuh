@@ -118,10 +118,11 @@ rollout_bwd_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
     const int n_last = a.N - (PPL - 1) * 32;
     const bool last_valid = lane < n_last;
 
-    const T* __restrict__ zmap = a.z + (long long)b * a.map_stride;
-    const T* __restrict__ fmap = a.mu + (long long)b * a.map_stride;
-    const T* __restrict__ cells = a.cells + (long long)b * a.cell_stride;
-    T* __restrict__ gmap = g.g_maps ? g.g_maps + (long long)b * g.g_maps_stride : nullptr;
+    const long long mi = b / a.map_group;                       // map of this trajectory (groups of consecutive trajectories share one)
+    const T* __restrict__ zmap = a.z + mi * a.map_stride;
+    const T* __restrict__ fmap = a.mu + mi * a.map_stride;
+    const T* __restrict__ cells = a.cells + mi * a.cell_stride;
+    T* __restrict__ gmap = g.g_maps ? g.g_maps + mi * g.g_maps_stride : nullptr;
     extern __shared__ __align__(16) unsigned char cache_raw[];
     MapGradCache<T>& wc = reinterpret_cast<MapGradCache<T>*>(cache_raw)[threadIdx.x >> 5];
     if (gmap) {

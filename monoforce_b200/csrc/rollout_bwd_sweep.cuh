@@ -228,12 +228,13 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
     const int b = blockIdx.x * kSweepWarps + warp;
     if (b >= a.B) return;
 
-    const T* __restrict__ zmap = a.z + (long long)b * a.map_stride;
-    const T* __restrict__ fmap = a.mu + (long long)b * a.map_stride;
-    const T* __restrict__ cells = a.cells + (long long)b * a.cell_stride;
-    T* __restrict__ gcell = g.g_cells ? g.g_cells + (long long)b * g.g_cells_stride : nullptr;
-    T* __restrict__ gz_dir = g.g_z ? g.g_z + (long long)b * g.g_dir_stride : nullptr;
-    T* __restrict__ gm_dir = g.g_mu ? g.g_mu + (long long)b * g.g_dir_stride : nullptr;
+    const long long mi = b / a.map_group;                       // map of this trajectory (groups of consecutive trajectories share one)
+    const T* __restrict__ zmap = a.z + mi * a.map_stride;
+    const T* __restrict__ fmap = a.mu + mi * a.map_stride;
+    const T* __restrict__ cells = a.cells + mi * a.cell_stride;
+    T* __restrict__ gcell = g.g_cells ? g.g_cells + mi * g.g_cells_stride : nullptr;
+    T* __restrict__ gz_dir = g.g_z ? g.g_z + mi * g.g_dir_stride : nullptr;
+    T* __restrict__ gm_dir = g.g_mu ? g.g_mu + mi * g.g_dir_stride : nullptr;
 
     extern __shared__ __align__(16) unsigned char cache_raw[];
     // per contact point one 3-quad record: [0] d/dz of the corners of the point's current cell, [1] d/dfriction of the

@@ -21,7 +21,8 @@ template <typename T>
 struct RolloutArgs {
     // geometry / problem size
     int B, nT, N, H, W, n_tracks;
-    long long map_stride;        // elements between two trajectories' maps, 0 = one shared map
+    long long map_stride;        // elements between two consecutive maps, 0 = one shared map
+    int map_group;               // consecutive trajectories that read the same map (>= 1): trajectory b uses map b / map_group
     // constants (dphys_config.py:77-153), already converted to T the way torch converts python scalars
     T mass, inv_mass, mg, stiffness, damping, res, inv_res, d_max, dt, omega_max, half_Ly, delta_h;
     T Iinv[9];                   // inverse inertia tensor, row-major (dphysics.py:152-153)

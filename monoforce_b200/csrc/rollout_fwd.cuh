@@ -92,9 +92,10 @@ rollout_fwd_kernel(const RolloutArgs<T> a) {
     T* const img_s = reinterpret_cast<T*>(stage_raw) + (size_t)(threadIdx.x >> 5) * 2 * row_stride;   // F_spring row image
     T* const img_f = img_s + row_stride;                                                                 // F_friction row image
 
-    const T* __restrict__ zmap = a.z + (long long)b * a.map_stride;
-    const T* __restrict__ fmap = a.mu + (long long)b * a.map_stride;
-    const T* __restrict__ cells = a.cells + (long long)b * a.cell_stride;
+    const long long mi = b / a.map_group;                       // map of this trajectory (groups of consecutive trajectories share one)
+    const T* __restrict__ zmap = a.z + mi * a.map_stride;
+    const T* __restrict__ fmap = a.mu + mi * a.map_stride;
+    const T* __restrict__ cells = a.cells + mi * a.cell_stride;
     const T* __restrict__ ctrl = a.controls + (long long)b * a.nT * 2;
     const int H = a.H, W = a.W;
 

@@ -97,7 +97,7 @@ def _ptr(t):
 class _RolloutMeta:
     """Everything that is not a differentiable tensor."""
     __slots__ = ("desc", "points", "part_id", "ts", "want_forces", "want_cost", "dtype_code", "B", "T", "N", "timings",
-                 "use_tape")
+                 "use_tape", "cost_buffer")
 
 
 def _require_cuda(*tensors):
@@ -140,7 +140,9 @@ class _Rollout(torch.autograd.Function):
         Fs = new(B, T, N, 3) if meta.want_forces else None
         Ff = new(B, T, N, 3) if meta.want_forces else None
         x0z = new(B)
-        cost = new(B) if meta.want_cost else None
+        cost = None
+        if meta.want_cost:
+            cost = meta.cost_buffer if meta.cost_buffer is not None else new(B)
         # adjoint tape (4 bytes per trajectory-step): only when a backward can follow
         csum = new(B, T) if meta.use_tape else None
         ws = _workspace(lib, meta, dev)
@@ -182,8 +184,14 @@ class _Rollout(torch.autograd.Function):
         gXs, gXds, gRs, gOms, gFs, gFf, gx0z = map(c, (gXs, gXds, gRs, gOms, gFs, gFf, gx0z))
         if not meta.want_forces:
             gFs = gFf = None
-        g_z = torch.zeros_like(z) if need[0] else None
-        g_mu = torch.zeros_like(mu) if need[1] else None
+        if need[0] and need[1] and z.shape == mu.shape:
+            # both map gradients in ONE buffer (two contiguous halves): a data-parallel caller all-reduces them as a
+            # single flat tensor without a gather / scatter copy (monoforce_b200/dist.py::allreduce_map_grads)
+            g_both = torch.zeros((2,) + tuple(z.shape), dtype=dt_, device=dev)
+            g_z, g_mu = g_both[0], g_both[1]
+        else:
+            g_z = torch.zeros_like(z) if need[0] else None
+            g_mu = torch.zeros_like(mu) if need[1] else None
         g_c = torch.empty_like(controls) if need[2] else None
         g_x0 = torch.empty_like(x0) if need[3] else None
         g_xd0 = torch.empty_like(xd0) if need[4] else None
@@ -226,6 +234,9 @@ class DPhysics(torch.nn.Module):
       * ``fused_cost`` (False): when True the kernel also emits the per-trajectory traversal
         cost ``norm(F_springs).std(-1).std(-1)`` (monoforce_node.py:91) in ``last_cost``.
       * ``timings`` (None): set to a list to collect CUDA events around each library call.
+      * ``shared_map`` (None): B `repeat`ed copies of one map are detected on the device and read as ONE shared map
+        (bit-identical results, no B cell tables); True promises it without looking, False disables the test.
+      * z_grid / friction with M maps for B = k*M trajectories: k consecutive trajectories share each map.
       * ``adjoint_tape`` (True): record the per-step soft-contact normaliser (4 B per trajectory-step) when
         gradients are required, which lets the backward run the single-sweep adjoint kernel.
     """
@@ -251,6 +262,8 @@ class DPhysics(torch.nn.Module):
         self.return_forces = True
         self.fused_cost = False
         self.last_cost = None
+        self.cost_buffer = None   # optional (B,) tensor the fused cost is written into (e.g. this rank's slice of an all-gather buffer)
+        self.shared_map = None    # None: recognise B repeated copies of one map on the device; True / False: caller's word
         self.adjoint_tape = True  # False: no contact_sum tape, the backward runs the three-pass adjoint (development / tests)
         self.timings = None      # set to a list to collect (name, start_event, end_event) around every library call
         self._const_cache = {}
@@ -293,6 +306,7 @@ class DPhysics(torch.nn.Module):
         desc.n_tracks = len(cfg.driving_parts)
         desc.variant = variant
         desc.map_stride = 0 if z.shape[0] == 1 else H * W
+        desc.traj_per_map = 0 if z.shape[0] in (1, B) else B // z.shape[0]
         desc.mass, desc.gravity = float(cfg.robot_mass), float(cfg.gravity)
         desc.stiffness, desc.damping = float(self.stiffness), float(self.damping)
         desc.grid_res, desc.d_max, desc.dt = float(cfg.grid_res), float(cfg.d_max), float(cfg.dt)
@@ -319,6 +333,10 @@ class DPhysics(torch.nn.Module):
         meta.dtype_code = _lib.MFB_F32 if dtype == torch.float32 else _lib.MFB_F64
         meta.B, meta.T, meta.N = B, T, pts.shape[0]
         meta.timings = self.timings
+        cb = self.cost_buffer
+        if cb is not None and not (cb.shape == (B,) and cb.dtype == dtype and cb.device == dev and cb.is_contiguous()):
+            raise ValueError(f"cost_buffer must be a contiguous ({B},) {dtype} tensor on {dev}")
+        meta.cost_buffer = cb
         cast = lambda t: t.to(device=dev, dtype=dtype)
         # contact_sum tape for the single-sweep adjoint: only when a backward can follow this call
         meta.use_tape = bool(self.adjoint_tape) and torch.is_grad_enabled() and any(
@@ -329,22 +347,56 @@ class DPhysics(torch.nn.Module):
         self.last_cost = cost if meta.want_cost else None
         return Xs, Xds, Rs, Oms, Fs, Ff
 
-    @staticmethod
-    def _shared_view(grid, B):
-        """(1,H,W) view when all B trajectories read one map (broadcast or `expand`ed input)."""
+    def _shared_view(self, grid, B):
+        """(1,H,W) view when all B trajectories read one map: a broadcast / `expand`ed input, or - what the reference's
+        callers pass (monoforce_node.py:156, diff_physics.ipynb cell 3) - B materialised `repeat`s of one map.  Repeats
+        are recognised by comparing all copies with the first on the device (one pass over the maps + one host read per
+        call: far cheaper than B cell tables) when no gradient can flow into the copies; `self.shared_map = True / False`
+        overrides the test (True is a promise by the caller, False never looks)."""
         if grid.shape[0] == 1:
             return grid
         if grid.stride(0) == 0:
             return grid[:1]
+        hint = self.shared_map
+        if hint is True:
+            return grid[:1]
+        if hint is None and grid.shape[0] == B and B > 1 and not (torch.is_grad_enabled() and grid.requires_grad):
+            if bool((grid == grid[:1]).all()):
+                return grid[:1]
         return grid
+
+    def _compute_device(self):
+        """The CUDA device the kernels run on.  `DPhysics(cfg)` with the reference's default device='cpu'
+        (scripts/fit_terrain.py:34) means HOST tensors in and out: they are staged through cuda:<current> (differentiable
+        `.to()` copies) - the arithmetic is still the sm_100a kernels, there is no CPU implementation to fall back to."""
+        d = torch.device(self.device)
+        if d.type == 'cuda':
+            return d
+        if not torch.cuda.is_available():
+            raise RuntimeError("monoforce_b200.DPhysics needs a CUDA device (sm_100a kernels, no CPU fallback); "
+                               "torch.cuda.is_available() is False")
+        return torch.device('cuda', torch.cuda.current_device())
 
     def dphysics(self, z_grid, controls, joint_angles=None, state=None, friction=None):
         """dphysics.py:530-594.  `z_grid` / `friction` may also be given as (1,H,W): one map shared
         by all `controls.shape[0]` trajectories (the reference's callers pass B copies)."""
         cfg = self.dphys_cfg
         dt, T = cfg.dt, cfg.traj_sim_time
+        # the reference reads integration_mode in update_state (:282-284, 'euler' | 'rk4') and hands it to torchdiffeq as
+        # `method` (:510-511); both kernels implement Euler only, so anything else must not silently run as Euler
+        mode = getattr(cfg, 'integration_mode', 'euler')
+        if mode != 'euler':
+            if mode != 'rk4' and not cfg.use_odeint:
+                raise ValueError(f'Unknown integration mode: {mode}')          # dphysics.py:382
+            raise NotImplementedError(
+                f"integration_mode={mode!r} is not implemented by the sm_100a rollout kernels (Euler only, which is what "
+                f"every caller of the reference uses); refusing to run it as Euler")
+        host_io = torch.device(self.device).type != 'cuda'
         controls = torch.as_tensor(controls).to(self.device)
-        batch_size = z_grid.shape[0] if z_grid.shape[0] != 1 else controls.shape[0]
+        # the reference takes B from z_grid.shape[0] (:551).  Extension: M maps for B = k*M control sequences means
+        # "k consecutive trajectories per map" (one map per scene, many shots per scene); M == 1 is one shared map
+        M, Bc = z_grid.shape[0], controls.shape[0]
+        batch_size = Bc if (M != Bc and Bc % M == 0) else M
         dtype = controls.dtype
 
         if state is None:                                                       # :554-559
@@ -355,19 +407,6 @@ class DPhysics(torch.nn.Module):
             omega = torch.zeros_like(x)
             omega[:, 2] = controls[:, 0, 1]
             state = (x, xd, R, omega)
-
-        if friction is None:                                                    # :562 (no B copies: stride-0 view)
-            friction = cfg.friction.to(self.device).unsqueeze(0)
-        self.z_grid = z_grid.to(self.device)                                    # :563-564
-        self.friction = friction.to(self.device)
-        self._z_arg = self._shared_view(self.z_grid, batch_size)
-        self._mu_arg = self._shared_view(self.friction, batch_size)
-        if self._z_arg.shape[0] != self._mu_arg.shape[0]:
-            # one shared + one per-trajectory map: materialise the shared one
-            if self._z_arg.shape[0] == 1:
-                self._z_arg = self._z_arg.expand(batch_size, -1, -1).contiguous()
-            else:
-                self._mu_arg = self._mu_arg.expand(batch_size, -1, -1).contiguous()
 
         N_ts = min(int(T / dt), controls.shape[1])                              # :573
         B = state[0].shape[0]
@@ -385,12 +424,39 @@ class DPhysics(torch.nn.Module):
         if self.ts.shape[0] != N_ts:
             raise AssertionError(f'time grid has {self.ts.shape[0]} samples, need {N_ts}')
 
+        cdev = self._compute_device()
+        if friction is None:                                                    # :562 (no B copies: stride-0 view)
+            friction = cfg.friction.to(self.device).unsqueeze(0)
+        self.z_grid = z_grid.to(self.device)                                    # :563-564
+        self.friction = friction.to(self.device)
+        self._z_arg = self._shared_view(self.z_grid, batch_size).to(cdev)
+        self._mu_arg = self._shared_view(self.friction, batch_size).to(cdev)
+        nz, nm = self._z_arg.shape[0], self._mu_arg.shape[0]
+        if nz != nm:
+            # different sharing for height and friction: materialise the coarser one at the finer grouping
+            if max(nz, nm) % min(nz, nm) != 0:
+                raise AssertionError(f'z_grid has {nz} maps but friction has {nm}')
+            if nz < nm:
+                self._z_arg = torch.repeat_interleave(self._z_arg, nm // nz, dim=0)
+            else:
+                self._mu_arg = torch.repeat_interleave(self._mu_arg, nz // nm, dim=0)
+        if batch_size % self._z_arg.shape[0] != 0:
+            raise AssertionError(f'{self._z_arg.shape[0]} maps cannot be shared evenly by {batch_size} trajectories')
+
         integrator = self.dynamics_odeint if cfg.use_odeint else self.dynamics   # read at call time
-        Xs, Xds, Rs, Omegas, F_springs, F_frictions = integrator(state)
+        if host_io:
+            self.controls = controls.to(cdev)
+            try:
+                outs = integrator(tuple(s.to(cdev) for s in state))
+            finally:
+                self.controls = controls
+            Xs, Xds, Rs, Omegas, F_springs, F_frictions = (o.to(self.device) for o in outs)
+        else:
+            Xs, Xds, Rs, Omegas, F_springs, F_frictions = integrator(state)
 
         # the reference snaps the start height into the caller's tensor in place (:571)
         with torch.no_grad():
-            state[0][..., 2] = self._x0z.to(state[0].dtype)
+            state[0][..., 2] = self._x0z.to(device=state[0].device, dtype=state[0].dtype)
         return (Xs, Xds, Rs, Omegas), (F_springs, F_frictions)
 
     def forward(self, z_grid, controls, joint_angles=None, state=None, vis=False, friction=None):

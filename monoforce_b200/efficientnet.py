@@ -18,6 +18,7 @@ Details that matter for numerics:
 from __future__ import annotations
 
 import math
+import warnings
 from collections import namedtuple
 
 import torch
@@ -239,7 +240,19 @@ class EfficientNet(nn.Module):
         weights come from `weights_path` (a state_dict file) or stay randomly initialised."""
         model = cls.from_name(model_name, in_channels=in_channels)
         if weights_path:
-            model.load_state_dict(torch.load(weights_path, map_location="cpu"))
+            state = torch.load(weights_path, map_location="cpu")
+            if in_channels != 3:       # efficientnet_pytorch re-creates the stem for other channel counts
+                state = {k: v for k, v in state.items() if not k.startswith("_conv_stem.")}
+            missing, unexpected = model.load_state_dict(state, strict=False)
+            if unexpected or [k for k in missing if not k.startswith("_conv_stem.")]:
+                raise RuntimeError(f"{weights_path} is not an efficientnet_pytorch B0 state_dict: missing {missing}, "
+                                   f"unexpected {unexpected}")
+        else:
+            warnings.warn(
+                "EfficientNet.from_pretrained: no ImageNet weights file given (pass trunk_weights=... to LiftSplatShoot / "
+                "CamEncode or set MFB_EFFICIENTNET_B0_WEIGHTS to an efficientnet_pytorch 'efficientnet-b0' state_dict); "
+                "the trunk is RANDOMLY initialised, unlike the reference (lss.py:55). Loading a full monoforce checkpoint "
+                "afterwards (LiftSplatShoot.from_pretrained) overrides this.", RuntimeWarning, stacklevel=2)
         return model
 
     def extract_features(self, x):

@@ -1,8 +1,8 @@
 """physics_loss: the training objective that seeds the rollout adjoint.
 
 Mirrors `monoforce/src/monoforce/losses.py:102-138` (time-weighted MSE between predicted and
-ground-truth positions at the nearest predicted time stamps; optional rotation term omitted
-as in every shipped caller: train.py:405-406, fit_terrain.py:57).
+ground-truth positions at the nearest predicted time stamps; the optional rotation term, used only
+by scripts/eval.py:151, is a handful of torch ops on top).
 
 CUDA tensors go through ONE fused kernel (csrc/physics_loss.cu, C entry point `mfb_physics_loss`) that
 does the nearest-stamp search, the weighted squared residuals and d loss / d X_pred in the same pass,
@@ -18,9 +18,82 @@ import torch
 from . import _lib
 
 
+_INCREASING = {}      # (data_ptr, version, shape, stride) -> bool; one device->host read per distinct stamp tensor
+
+
+def _strictly_increasing(ts):
+    key = (ts.data_ptr(), ts._version, tuple(ts.shape), ts.stride(), str(ts.device))
+    hit = _INCREASING.get(key)
+    if hit is None:
+        if len(_INCREASING) > 64:
+            _INCREASING.clear()
+        hit = bool((ts[..., 1:] > ts[..., :-1]).all()) if ts.shape[-1] > 1 else True
+        _INCREASING[key] = hit
+    return hit
+
+
 def _same_grid(pred_ts, gt_ts):
-    return (pred_ts is gt_ts) or (pred_ts.shape == gt_ts.shape and pred_ts.data_ptr() == gt_ts.data_ptr()
+    """True when the nearest-stamp gather (losses.py:116-119) is provably the identity: both arguments are the same
+    storage AND the stamps are strictly increasing (with duplicated stamps argmin returns the FIRST of the ties, which
+    is not the identity)."""
+    same = (pred_ts is gt_ts) or (pred_ts.shape == gt_ts.shape and pred_ts.data_ptr() == gt_ts.data_ptr()
                                   and pred_ts.stride() == gt_ts.stride())
+    return same and _strictly_increasing(gt_ts)
+
+
+def rotation_difference(R1, R2, reduction='mean'):
+    """Squared geodesic angle between rotations (losses.py:48-65)."""
+    assert R1.shape == R2.shape and R1.shape[-2:] == (3, 3)
+    dR = R1 @ R2.transpose(dim0=-2, dim1=-1)
+    tr = dR.diagonal(dim1=-2, dim2=-1).sum(dim=-1, keepdim=True)
+    theta = torch.arccos(torch.clip((tr - 1) / 2., min=-1, max=1.)) ** 2
+    if reduction == 'mean':
+        return theta.mean()
+    if reduction == 'sum':
+        return theta.sum()
+    return theta
+
+
+def translation_difference(x1, x2, reduction='mean'):
+    """losses.py:36-45."""
+    assert x1.shape == x2.shape and x1.shape[-1] == 3
+    d = torch.norm(x1 - x2, dim=-1)
+    return d.mean() if reduction == 'mean' else d.sum() if reduction == 'sum' else d
+
+
+def total_variation(heightmap):
+    """losses.py:68-74 (fit_terrain.py:58)."""
+    h, w = heightmap.shape[-2:]
+    tv = torch.sum(torch.abs(heightmap[..., :, :-1] - heightmap[..., :, 1:])) + \
+        torch.sum(torch.abs(heightmap[..., :-1, :] - heightmap[..., 1:, :]))
+    return tv / (h * w)
+
+
+def hm_loss(height_pred, height_gt, weights=None, h_max=None):
+    """Weighted MSE between height maps, NaN cells ignored - losses.py:77-99 (train.py:387-395)."""
+    assert height_pred.shape == height_gt.shape, 'Height prediction and ground truth must have the same shape'
+    if weights is None:
+        weights = torch.ones_like(height_gt)
+    assert weights.shape == height_gt.shape, 'Weights and height ground truth must have the same shape'
+    if h_max is not None:
+        height_pred = h_max * torch.tanh(height_pred)
+    valid = ~(torch.isnan(height_pred) | torch.isnan(height_gt))
+    height_gt, height_pred, weights = height_gt[valid], height_pred[valid], weights[valid]
+    return ((height_pred * weights - height_gt * weights) ** 2).mean()
+
+
+def _rotation_term(states_pred, states_gt, pred_ts, gt_ts, gamma):
+    """losses.py:129-134 (torch ops: eval.py:151 is the only caller; not on the training hot path)."""
+    R = states_gt[2]
+    dev = R.device
+    pred_ts, gt_ts = pred_ts.to(dev), gt_ts.to(dev)
+    if _same_grid(pred_ts, gt_ts) and states_pred[2].shape[1] == gt_ts.shape[-1]:
+        R_pred = states_pred[2]
+    else:
+        ts_ids = torch.argmin(torch.abs(pred_ts.unsqueeze(1) - gt_ts.unsqueeze(2)), dim=2)
+        R_pred = states_pred[2][torch.arange(R.shape[0], device=dev).unsqueeze(1), ts_ids]
+    time_weights = 1. / (1. + gamma * gt_ts.unsqueeze(2))
+    return (rotation_difference(R_pred, R, reduction='none') * time_weights).mean()
 
 
 class _FusedPhysicsLoss(torch.autograd.Function):
@@ -77,8 +150,7 @@ def _host_physics_loss(X_pred, X, pred_ts, gt_ts, gamma):
 
 
 def physics_loss(states_pred, states_gt, pred_ts, gt_ts, gamma=0.9, rotation_loss=False):
-    if rotation_loss:
-        raise NotImplementedError("rotation_loss=True is not used by any caller on the hot path")
+    """losses.py:102-138.  Returns `loss`, or `(loss, loss_rot)` with rotation_loss=True (scripts/eval.py:151)."""
     X = states_gt[0]
     X_pred = states_pred[0]
     if X_pred.is_cuda:
@@ -87,5 +159,9 @@ def physics_loss(states_pred, states_gt, pred_ts, gt_ts, gamma=0.9, rotation_los
         if X.requires_grad:
             raise NotImplementedError("physics_loss: gradients w.r.t. the ground-truth states are not provided by the "
                                       "fused kernel (no caller of the reference differentiates them)")
-        return _FusedPhysicsLoss.apply(X_pred, X, pred_ts, gt_ts, gamma)
-    return _host_physics_loss(X_pred, X, pred_ts, gt_ts, gamma)
+        loss = _FusedPhysicsLoss.apply(X_pred, X, pred_ts, gt_ts, gamma)
+    else:
+        loss = _host_physics_loss(X_pred, X, pred_ts, gt_ts, gamma)
+    if rotation_loss:
+        return loss, _rotation_term(states_pred, states_gt, pred_ts, gt_ts, gamma)
+    return loss

@@ -20,6 +20,7 @@ The frustum geometry (`get_geometry`, lss.py:204-224) is a handful of tiny 3x3 o
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -104,13 +105,16 @@ def _to_nhwc_bf16(x, c_padded):
 
 
 def _folded(module, build):
-    """Per-module cache of folded (weights, scale, shift); dropped whenever train() / eval() is toggled."""
+    """Per-module cache of folded (weights, scale, shift), keyed on `params_stamp(module)`: storage addresses + in-place
+    version counters of every parameter / buffer, so load_state_dict / from_pretrained / an optimizer step invalidate
+    it (as EfficientNet.folded and BevEncode.fast_backbone_endpoints do)."""
+    stamp = params_stamp(module)
     cache = module.__dict__.get("_mfb_folded")
-    if cache is None:
+    if cache is None or cache[0] != stamp:
         with torch.no_grad():
-            cache = build()
+            cache = (stamp, build())
         module.__dict__["_mfb_folded"] = cache
-    return cache
+    return cache[1]
 
 
 class CamEncode(nn.Module):
@@ -119,10 +123,14 @@ class CamEncode(nn.Module):
     fused lift-splat kernel.  `get_depth_feat` keeps the reference's materialising behaviour for callers
     that want the lifted tensor."""
 
-    def __init__(self, D, C, in_channels=3):
+    def __init__(self, D, C, in_channels=3, trunk_weights=None):
         super().__init__()
         self.D, self.C = D, C
-        self.trunk = EfficientNet.from_pretrained("efficientnet-b0", in_channels=in_channels)
+        # lss.py:55 starts from ImageNet weights (efficientnet_pytorch downloads them).  No network here: the file comes
+        # from `trunk_weights` or $MFB_EFFICIENTNET_B0_WEIGHTS (an efficientnet_pytorch state_dict); without one the trunk
+        # is randomly initialised and from_pretrained says so loudly.
+        self.trunk = EfficientNet.from_pretrained("efficientnet-b0", in_channels=in_channels,
+                                                  weights_path=trunk_weights or os.environ.get("MFB_EFFICIENTNET_B0_WEIGHTS"))
         self.up1 = Up(320 + 112, 512)
         self.depthnet = nn.Conv2d(512, self.D + self.C, kernel_size=1, padding=0)
 
@@ -293,7 +301,7 @@ class _LiftSplat(torch.autograd.Function):
 
 
 class LiftSplatShoot(nn.Module):
-    def __init__(self, grid_conf, data_aug_conf, outC=1):
+    def __init__(self, grid_conf, data_aug_conf, outC=1, trunk_weights=None):
         super().__init__()
         self.grid_conf = grid_conf
         self.data_aug_conf = data_aug_conf
@@ -305,7 +313,7 @@ class LiftSplatShoot(nn.Module):
         self.camC = 64
         self.frustum = self.create_frustum()
         self.D = self.frustum.shape[0]
-        self.camencode = CamEncode(self.D, self.camC)
+        self.camencode = CamEncode(self.D, self.camC, trunk_weights=trunk_weights)
         self.bevencode = BevEncode(inC=self.camC, outC=outC)
         self.use_quickcumsum = True      # kept for attribute compatibility; the fused kernel needs neither path
         self.fast_inference = False      # opt-in: bf16 tcgen05 path for the dense layers (eval mode only)
@@ -347,6 +355,29 @@ class LiftSplatShoot(nn.Module):
         flat = idx[..., 0] * nx[1] + idx[..., 1]
         return torch.where(ok, flat, torch.full_like(flat, -1)).to(torch.int32).contiguous()
 
+    def cached_voxel_index(self, rots, trans, intrins, post_rots, post_trans):
+        """`voxel_index(get_geometry(...))` depends only on the calibration (lss.py:204-224,246-257), which is static
+        per rig: it is computed once per distinct calibration and reused, so the (B,N,D,fH,fW,3) geometry tensor (45 MB
+        at 16 scenes x 512^2) is not re-materialised every forward.  Look-up: (i) the same tensors (storage + version) as
+        the previous call - no device work at all; (ii) otherwise by the calibration VALUES (one small device->host read
+        of B*N*33 floats), which also catches callers that rebuild the tensors for every frame."""
+        cal = (rots, trans, intrins, post_rots, post_trans)
+        ident = tuple((t.data_ptr(), t._version, tuple(t.shape), str(t.device)) for t in cal)
+        cache = self.__dict__.setdefault("_mfb_vox_cache", {"ident": None, "by_value": {}})
+        if cache["ident"] is not None and cache["ident"][0] == ident:
+            return cache["ident"][1]
+        key = (str(rots.device), self.frustum.shape,
+               torch.cat([t.detach().reshape(-1).float() for t in cal]).cpu().numpy().tobytes())
+        vox = cache["by_value"].get(key)
+        if vox is None:
+            if len(cache["by_value"]) >= 8:
+                cache["by_value"].clear()
+            with torch.no_grad():
+                vox = self.voxel_index(self.get_geometry(*cal))
+            cache["by_value"][key] = vox
+        cache["ident"] = (ident, vox)
+        return vox
+
     def get_cam_feats(self, x):
         """Reference-compatible lifted tensor (B, N, D, fH, fW, C) - lss.py:226-236 (materialises it)."""
         B, N, Cin, H, W = x.shape
@@ -360,7 +391,7 @@ class LiftSplatShoot(nn.Module):
             raise NotImplementedError("the fused lift-splat kernel assumes a single z voxel (zbound of lss_cfg.yaml)")
         if not x.is_cuda:
             raise RuntimeError("monoforce_b200.LiftSplatShoot runs on CUDA only (fused lift-splat kernel, no CPU fallback)")
-        vox = self.voxel_index(self.get_geometry(rots, trans, intrins, post_rots, post_trans))
+        vox = self.cached_voxel_index(rots, trans, intrins, post_rots, post_trans)
         if self._fast():
             logits = self.camencode.fast_logits_nhwc(x.view(B * N, Cin, H, W))
         else:

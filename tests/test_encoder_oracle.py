@@ -126,3 +126,70 @@ def test_folded_inference_weights_match_module_path():
         y0 = t._swish(t._bn0(t._conv_stem(x)))
         f0 = torch.nn.functional.silu(torch.nn.functional.conv2d(torch.nn.functional.pad(x, (0, 1, 0, 1)), *t.folded(torch.float32)["stem"], 2))
         assert rel(f0, y0) < 1e-5
+
+
+def test_efficientnet_restatement_is_structurally_torchvision_b0():
+    """The trunk internals cannot be pinned against efficientnet_pytorch 0.7.1 (absent from /root/reference and from this
+    image), so they are anchored against an INDEPENDENT implementation of the same published architecture:
+    torchvision.models.efficientnet_b0.  Weights are copied across key by key (which proves every block's kernel size,
+    stride, expansion, squeeze-excite width and channel count), then the two networks must produce the same five
+    endpoint feature maps.  The only modelled difference between the two packages is the padding convention of the four
+    stride-2 layers (TF 'SAME' = (0,1)/(1,2) here, symmetric in torchvision); for this comparison our stride-2 pads are
+    switched to symmetric, and the 'SAME' rule itself is checked against its closed form below."""
+    from functools import partial
+    import torchvision
+    from monoforce_b200.efficientnet import EfficientNet, _same_pad
+    torch.manual_seed(0)
+    tv = torchvision.models.efficientnet_b0(weights=None, norm_layer=partial(torch.nn.BatchNorm2d, eps=1e-3, momentum=0.01)).eval()
+    ours = EfficientNet.from_name("efficientnet-b0").eval()
+    assert sum(p.numel() for p in tv.parameters()) == sum(p.numel() for p in ours.parameters()) == 5_288_548
+    with torch.no_grad():
+        for m in tv.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.3); m.running_var.uniform_(0.5, 1.5); m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.2)
+
+    def cp(dst, src):
+        assert {k: tuple(v.shape) for k, v in dst.state_dict().items()} == {k: tuple(v.shape) for k, v in src.state_dict().items()}
+        dst.load_state_dict(src.state_dict())
+    cp(ours._conv_stem, tv.features[0][0]); cp(ours._bn0, tv.features[0][1])
+    tv_blocks = [b for stage in tv.features[1:8] for b in stage]
+    assert len(tv_blocks) == len(ours._blocks) == 16
+    for mine, theirs in zip(ours._blocks, tv_blocks):
+        parts = list(theirs.block)
+        a = mine._block_args
+        if a.expand_ratio != 1:
+            e = parts.pop(0)
+            cp(mine._expand_conv, e[0]); cp(mine._bn0, e[1])
+            assert isinstance(e[2], torch.nn.SiLU)
+        dw, se, pr = parts
+        assert dw[0].kernel_size == (a.kernel_size,) * 2 and dw[0].stride == (a.stride,) * 2 and dw[0].groups == dw[0].in_channels
+        cp(mine._depthwise_conv, dw[0]); cp(mine._bn1, dw[1])
+        cp(mine._se_reduce, se.fc1); cp(mine._se_expand, se.fc2)
+        assert isinstance(se.activation, torch.nn.SiLU) and isinstance(se.scale_activation, torch.nn.Sigmoid)
+        cp(mine._project_conv, pr[0]); cp(mine._bn2, pr[1])
+        assert len(pr) == 2                                          # no activation after the projection
+        assert theirs.use_res_connect == (a.id_skip and a.stride == 1 and a.input_filters == a.output_filters)
+    cp(ours._conv_head, tv.features[8][0]); cp(ours._bn1, tv.features[8][1])
+    # TF 'SAME' at the nominal 224 input (what Conv2dStaticSamePadding bakes in): stride-1 symmetric, stride-2 one more
+    # pixel after than before
+    assert _same_pad(224, 3, 2) == (0, 1) and _same_pad(112, 3, 1) == (1, 1) and _same_pad(56, 5, 2) == (1, 2)
+    assert _same_pad(28, 3, 2) == (0, 1) and _same_pad(14, 5, 1) == (2, 2) and _same_pad(14, 5, 2) == (1, 2)
+    n_sym = 0
+    for m in ours.modules():
+        if hasattr(m, "static_padding") and isinstance(m.static_padding, torch.nn.ZeroPad2d):
+            l, r, t, b = m.static_padding.padding
+            if l != r:
+                assert m.stride == (2, 2) and (l, r) == (t, b) == ((0, 1) if m.kernel_size[0] == 3 else (1, 2))
+                p = (m.kernel_size[0] - 1) // 2
+                m.static_padding = torch.nn.ZeroPad2d((p, p, p, p))
+                n_sym += 1
+    assert n_sym == 5                                                # stem + the four stride-2 depthwise convs
+    x = torch.randn(2, 3, 96, 128)
+    with torch.no_grad():
+        y = ours._swish(ours._bn0(ours._conv_stem(x)))
+        z = tv.features[0](x)
+        assert torch.allclose(y, z, rtol=1e-4, atol=1e-5)
+        for mine, theirs in zip(ours._blocks, tv_blocks):
+            y, z = mine(y), theirs(z)
+            assert y.shape == z.shape and torch.allclose(y, z, rtol=1e-4, atol=1e-4), mine._block_args
+        assert torch.allclose(ours._swish(ours._bn1(ours._conv_head(y))), tv.features[8](z), rtol=1e-4, atol=1e-4)

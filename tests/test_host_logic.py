@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.mfb_abi_version() == int(re.search(r"#define MFB_ABI_VERSION (\d+)", header).group(1)) == 2
+    assert lib.mfb_abi_version() == int(re.search(r"#define MFB_ABI_VERSION (\d+)", header).group(1)) == 3
 
 
 def test_ctypes_structs_mirror_the_header_field_for_field():
@@ -102,11 +102,105 @@ def test_module_surface_and_no_cpu_fallback():
     assert tv.shape == (1, 2) and tv[0, 0] < tv[0, 1]
     with pytest.raises(ValueError):
         vw_to_track_vels(torch.tensor([1.0]), torch.tensor([0.5]), cfg.robot_size, 3)
-    with pytest.raises(RuntimeError, match="CUDA only"):
-        sim(cfg.z_grid.repeat(3, 1, 1), controls)
+    if not torch.cuda.is_available():
+        # device='cpu' means host tensors in / out, staged through the GPU: without one it must fail loudly
+        with pytest.raises(RuntimeError, match="needs a CUDA device"):
+            sim(cfg.z_grid.repeat(3, 1, 1), controls)
     state = (torch.zeros(3, 3), torch.zeros(3, 3), torch.eye(3).repeat(3, 1, 1), torch.zeros(3, 3))
     with pytest.raises(AssertionError, match="Controls shape"):       # same message as dphysics.py:575
         sim(cfg.z_grid.repeat(3, 1, 1), controls[:2], state=state)
+
+
+def test_unsupported_integration_mode_is_refused_not_run_as_euler():
+    """ADVICE r1: the reference honours integration_mode ('rk4' in update_state :361-383, `method=` of odeint :510-511);
+    the kernels are Euler only, so any other mode must raise instead of silently producing Euler trajectories."""
+    from monoforce_b200 import DPhysics, DPhysConfig, generate_controls
+    cfg = DPhysConfig(robot="tradr", grid_res=0.4)
+    cfg.traj_sim_time = 0.2
+    controls, _ = generate_controls(n_trajs=2, time_horizon=0.2, dt=0.01)
+    for odeint in (False, True):
+        cfg.use_odeint, cfg.integration_mode = odeint, "rk4"
+        with pytest.raises(NotImplementedError, match="rk4"):
+            DPhysics(cfg, device="cpu")(cfg.z_grid.repeat(2, 1, 1), controls)
+    cfg.use_odeint, cfg.integration_mode = False, "midpoint"
+    with pytest.raises(ValueError, match="Unknown integration mode"):      # same error as dphysics.py:382
+        DPhysics(cfg, device="cpu")(cfg.z_grid.repeat(2, 1, 1), controls)
+
+
+def test_folded_weight_cache_follows_parameter_updates():
+    """the bf16 fold cache of Up / depthnet / heads must notice load_state_dict and in-place updates."""
+    from monoforce_b200.terrain_encoder import _folded
+    m = torch.nn.Conv2d(4, 4, 1)
+    calls = []
+    build = lambda: calls.append(1) or m.weight.detach().clone()
+    a = _folded(m, build)
+    assert _folded(m, build) is a and len(calls) == 1
+    with torch.no_grad():
+        m.weight.mul_(2.0)                                   # optimizer step / in-place edit
+    b = _folded(m, build)
+    assert len(calls) == 2 and torch.equal(b, m.weight)
+    m.load_state_dict({k: v * 0 + 1 for k, v in m.state_dict().items()})
+    c = _folded(m, build)
+    assert len(calls) == 3 and torch.equal(c, torch.ones_like(c))
+
+
+def test_efficientnet_trunk_weights_are_plumbed_and_absence_is_loud(tmp_path, monkeypatch):
+    """lss.py:55 starts from ImageNet weights; here a weights file can be passed (argument or environment
+    variable) and a missing one is announced instead of silently training from scratch."""
+    import warnings
+    from monoforce_b200.efficientnet import EfficientNet
+    from monoforce_b200.terrain_encoder import CamEncode
+    monkeypatch.delenv("MFB_EFFICIENTNET_B0_WEIGHTS", raising=False)
+    with pytest.warns(RuntimeWarning, match="RANDOMLY initialised"):
+        src = EfficientNet.from_pretrained("efficientnet-b0")
+    with torch.no_grad():
+        for p_ in src.parameters():
+            p_.add_(0.5)
+    f = tmp_path / "b0.pth"
+    torch.save(src.state_dict(), f)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        cam = CamEncode(8, 4, trunk_weights=str(f))
+        monkeypatch.setenv("MFB_EFFICIENTNET_B0_WEIGHTS", str(f))
+        cam2 = CamEncode(8, 4)
+    for k, v in src.state_dict().items():
+        assert torch.equal(cam.trunk.state_dict()[k], v) and torch.equal(cam2.trunk.state_dict()[k], v)
+    torch.save({"not": torch.zeros(1)}, f)
+    with pytest.raises(RuntimeError, match="not an efficientnet_pytorch"):
+        CamEncode(8, 4, trunk_weights=str(f))
+
+
+def test_physics_loss_rotation_term_and_duplicate_stamps():
+    """losses.py:129-136 (scripts/eval.py:151 unpacks two values) and the identity shortcut only for strictly
+    increasing stamps (argmin returns the first of tied stamps)."""
+    from monoforce_b200.losses import physics_loss, rotation_difference
+    from oracle.ref_import import reference_available
+    g = torch.Generator().manual_seed(1)
+    B, T = 3, 12
+    Xp, Xg = torch.randn(B, T, 3, generator=g), torch.randn(B, T, 3, generator=g)
+
+    def rots(n):
+        q, _ = torch.linalg.qr(torch.randn(B, n, 3, 3, generator=g))
+        return q * torch.sign(torch.linalg.det(q))[..., None, None]
+    Rp, Rg = rots(T), rots(T)
+    ts = torch.arange(T, dtype=torch.float32)[None] * 0.1
+    loss, loss_rot = physics_loss((Xp, None, Rp), (Xg, None, Rg), ts, ts, 0.9, rotation_loss=True)
+    w = 1. / (1. + 0.9 * ts.unsqueeze(2))
+    assert torch.allclose(loss_rot, (rotation_difference(Rp, Rg, reduction='none') * w).mean())
+    assert torch.allclose(loss, ((Xp * w - Xg * w) ** 2).mean())
+    dup = ts.clone()
+    dup[0, 5] = dup[0, 4]                                   # tie: the reference gathers index 4 for stamp 5
+    ids = torch.argmin(torch.abs(dup.unsqueeze(1) - dup.unsqueeze(2)), dim=2)
+    ref = ((Xp[torch.arange(B).unsqueeze(1), ids] * (1. / (1. + 0.9 * dup.unsqueeze(2))) - Xg * (1. / (1. + 0.9 * dup.unsqueeze(2)))) ** 2).mean()
+    assert torch.allclose(physics_loss((Xp,), (Xg,), dup, dup, 0.9), ref)
+    if reference_available():
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_ref_losses_t", "/root/reference/monoforce/src/monoforce/losses.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        rl, rr = mod.physics_loss((Xp, None, Rp), (Xg, None, Rg), ts, ts, 0.9, rotation_loss=True)
+        assert torch.allclose(loss, rl) and torch.allclose(loss_rot, rr)
+        assert torch.allclose(physics_loss((Xp,), (Xg,), dup, dup, 0.9), mod.physics_loss((Xp,), (Xg,), dup, dup, 0.9))
 
 
 def test_physics_loss_matches_reference_definition():
@@ -150,6 +244,13 @@ def _worker(rank, world, port, n, q):
     g2 = torch.arange(3, dtype=torch.float32) * (rank + 1)                   # second map: both travel as one flat all-reduce
     allreduce_map_grads(g, None, g2)
     ok_g2 = torch.equal(g2, torch.arange(3, dtype=torch.float32) * 3) and g.shape == (4, 4) and bool((g == g[0, 0]).all())
+    # the two halves of one buffer (what DPhysics' backward returns) are reduced in place through one flat view
+    both = torch.stack([torch.full((2, 5), float(rank + 1)), torch.full((2, 5), 10.0 * (rank + 1))])
+    ptr = both.data_ptr()
+    allreduce_map_grads(both[0], both[1])
+    ok_g2 = ok_g2 and both.data_ptr() == ptr and bool((both[0] == 3).all()) and bool((both[1] == 30).all())
+    from monoforce_b200.dist import _adjacent_view
+    ok_g2 = ok_g2 and _adjacent_view([both[0], both[1]]) is not None and _adjacent_view([both[1], both[0]]) is None
     q.put((rank, torch.equal(gathered, all_costs) and ok_g2, idx, val, float(g[0, 0])))
     dist.destroy_process_group()
 
