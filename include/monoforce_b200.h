@@ -151,13 +151,67 @@ int mfb_lift_splat_forward(const void* logits, const void* vox, void* bev, int B
                            int fH, int fW, int X, int Y, void* stream);
 int mfb_lift_splat_backward(const void* logits, const void* vox, const void* g_bev, void* g_logits,
                             int B, int N, int D, int C, int fH, int fW, int X, int Y, void* stream);
+/* Forward on bf16 logits rows of `row_stride` scalars (>= D + C): the tensor-core depthnet writes 128-channel bf16 rows. */
+int mfb_lift_splat_forward_bf16(const void* logits, int row_stride, const void* vox, void* bev, int B, int N, int D, int C,
+                                int fH, int fW, int X, int Y, void* stream);
+
+/* ---- terrain encoder: memory-bound NHWC bf16 layers between the tensor-core convolutions (csrc/encoder_ops.cu) ----------
+ * All tensors NHWC bf16 unless stated, channel counts multiples of 8, 16-byte aligned, asynchronous on `stream`.
+ *
+ * mfb_upsample_concat_nhwc_bf16: out[n,h,w,:] = [skip[n,h,w,:C_skip], bilinear_upsample(low)[n,h,w,:C_low], 0...] - the
+ *   `torch.cat([x2, self.up(x1)], dim=1)` of Up.forward (lss.py:44-46; nn.Upsample(bilinear, align_corners=True)) and, with
+ *   C_skip = 0, the x2 up-sampling in front of the BEV heads (lss.py:118,126,133).
+ * mfb_stem_conv_bf16: EfficientNet-B0 stem (efficientnet_pytorch 0.7.1 `_conv_stem` + `_bn0` + swish, lss.py:78):
+ *   img (N,3,H,W) fp32 NCHW -> y (N,Ho,Wo,32); w (3,3,3,32) fp32 [dy][dx][ci][co] with the BatchNorm scale folded in.
+ * mfb_dwconv_bn_silu_bf16: MBConv depthwise K x K (3 | 5) convolution, stride 1 | 2, low-side padding (pad_h, pad_w), folded
+ *   BatchNorm, swish; `pool` (N,C) fp32, if not NULL, accumulates the sum of the outputs over the pixels (the squeeze of the
+ *   squeeze-excite block; zero it first).  w (K*K, C) fp32, shift (C,) fp32.
+ * mfb_se_fold_bf16: s = sigmoid(W_expand swish(W_reduce (pool * inv_hw) + b_reduce) + b_expand) per image and
+ *   out_w[n,co,c] = proj_w[co,c] * s[c]: the excite scale folded into that image's projection matrix (consumed by
+ *   mfb_conv2d_bf16 with per_image_weights).  w_reduce (Sq,C_se), w_expand (C_se,Sq) fp32; channels [C_se, C) are padding.
+ * mfb_cast_f32_to_bf16: n scalars (multiple of 8). */
+int mfb_upsample_concat_nhwc_bf16(const void* skip, const void* low, void* out, int N, int H, int W, int C_skip, int Hl,
+                                  int Wl, int C_low, int C_out, void* stream);
+int mfb_stem_conv_bf16(const void* img, const void* w, const void* shift, void* y, int N, int H, int W, int Ho, int Wo,
+                       int pad_h, int pad_w, void* stream);
+int mfb_dwconv_bn_silu_bf16(const void* x, const void* w, const void* shift, void* y, void* pool, int N, int H, int W, int C,
+                            int Ho, int Wo, int K, int stride, int pad_h, int pad_w, void* stream);
+int mfb_se_fold_bf16(const void* pool, float inv_hw, const void* w_reduce, const void* b_reduce, const void* w_expand,
+                     const void* b_expand, const void* proj_w, void* out_w, int N, int C, int C_se, int Sq, int Cout, void* stream);
+int mfb_cast_f32_to_bf16(const void* src, void* dst, long long n, void* stream);
 
 /* ---- terrain encoder: dense convolution on tcgen05 tensor cores ----------------------------
- * Replaces the Conv2d -> BatchNorm2d(eval) -> activation triples of the encoder's dense layers
- * (Up.conv terrain_encoder/lss.py:34-41, BevEncode heads lss.py:117-139, depthnet lss.py:58):
- *   y[n,h,w,co] = act(scale[co] * conv_KSxKS_same(x, wgt)[n,h,w,co] + shift[co])
- * x (N,H,W,Cin) and y (N,H,W,Cout) are NHWC bf16, wgt (Cout, KS, KS, Cin) bf16, scale/shift (Cout,) fp32.
- * KS in {1,3}, stride 1, zero padding KS/2, Cin % 64 == 0, Cout % 64 == 0; act: 0 none, 1 ReLU, 2 GELU(erf). */
+ * Replaces the Conv2d -> BatchNorm2d(eval) [-> + residual] -> activation groups of the encoder's GEMM-shaped layers:
+ *   Up.conv                                  terrain_encoder/lss.py:34-41
+ *   BevEncode conv1 7x7/2, ResNet-18 layer1-3 (torchvision BasicBlock: 3x3, 3x3/2, 1x1/2 downsample, add, ReLU)  lss.py:104-116,140-151
+ *   BevEncode heads incl. their 1x1 output convolution and ScaledTanh / ReLU   lss.py:117-139
+ *   depthnet                                 lss.py:58
+ *   EfficientNet-B0 MBConv 1x1 expand / project convolutions (efficientnet_pytorch 0.7.1, called from lss.py:73-94)
+ *
+ *   t[n,h,w,co] = scale[co] * sum_{dy,dx,ci} x[n, stride*h + dy - pad_h, stride*w + dx - pad_w, ci] * wgt[co,dy,dx,ci] + shift[co]
+ *   y           = act(t + residual)                                                  (n_heads == 0)
+ *   head_out[n,g,h,w] = head_act_g(sum_{c<G} act(t)[n,h,w,g*G+c] * head_w[g*G+c] + head_bias[g]),  G = Cout / n_heads   (n_heads > 0)
+ * x (N,H,W,Cin), y / residual (N,Ho,Wo,Cout) NHWC bf16; wgt (Cout,KH,KW,Cin) bf16, or (N,Cout,KH,KW,Cin) with
+ * per_image_weights (an MBConv block's squeeze-excite scale folded into its projection matrix per image);
+ * scale / shift / head_w fp32; head_out (N,n_heads,Ho,Wo) fp32.  Reads outside the image are zeros (the convolution's
+ * padding; pad_* is the LOW-side padding, the high side follows from Ho / Wo).
+ * Cin % 8 == 0, Cout % 8 == 0 (channels beyond the tensors' extent are zero-filled by TMA, nothing is padded in memory),
+ * KH, KW <= 7, stride 1 or 2; head mode needs G == 128 (G == 64 when Cout == 64). */
+typedef enum mfb_act { MFB_ACT_NONE = 0, MFB_ACT_RELU = 1, MFB_ACT_GELU = 2, MFB_ACT_SILU = 3 } mfb_act;
+typedef enum mfb_head_act { MFB_HEAD_NONE = 0, MFB_HEAD_RELU = 1, MFB_HEAD_SCALED_TANH = 2 /* lo + (hi-lo)(tanh x + 1)/2, lss.py:17-24 */ } mfb_head_act;
+typedef struct mfb_conv_desc {
+    int32_t N, H, W, Cin;
+    int32_t Ho, Wo, Cout;
+    int32_t KH, KW, stride, pad_h, pad_w;
+    int32_t act;                 /* mfb_act */
+    int32_t per_image_weights;   /* 0 / 1 */
+    int32_t n_heads;             /* 0: write y; 1..4: fused 1x1 heads, write head_out */
+    int32_t head_act[4];         /* mfb_head_act */
+    float head_bias[4], head_lo[4], head_hi[4];
+} mfb_conv_desc;
+int mfb_conv2d_bf16(const mfb_conv_desc* desc, const void* x, const void* wgt, const void* scale, const void* shift,
+                    const void* residual, void* y, const void* head_w, void* head_out, void* stream);
+/* ABI v2 form: KS x KS (1 or 3), stride 1, zero padding KS/2; act: 0 none, 1 ReLU, 2 GELU(erf). */
 int mfb_conv_bn_act_bf16(const void* x, const void* wgt, const void* scale, const void* shift, void* y,
                          int N, int H, int W, int Cin, int Cout, int KS, int act, void* stream);
 

@@ -18,9 +18,17 @@ MFB_PHYSICS_LOSS_MAX_BLOCKS = 4096
 
 EXPORTED_SYMBOLS = (
     "mfb_rollout_workspace_bytes", "mfb_rollout_forward", "mfb_rollout_backward", "mfb_rollout_forward_host",
-    "mfb_lift_splat_forward", "mfb_lift_splat_backward", "mfb_conv_bn_act_bf16", "mfb_physics_loss",
+    "mfb_lift_splat_forward", "mfb_lift_splat_backward", "mfb_lift_splat_forward_bf16", "mfb_conv_bn_act_bf16",
+    "mfb_conv2d_bf16", "mfb_upsample_concat_nhwc_bf16", "mfb_stem_conv_bf16", "mfb_dwconv_bn_silu_bf16", "mfb_se_fold_bf16",
+    "mfb_cast_f32_to_bf16", "mfb_physics_loss",
     "mfb_last_error", "mfb_abi_version", "mfb_kernel_launches", "mfb_release_scratch",
 )
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("N", "H", "W", "Cin", "Ho", "Wo", "Cout", "KH", "KW", "stride", "pad_h", "pad_w",
+                                         "act", "per_image_weights", "n_heads")] + \
+               [("head_act", C.c_int32 * 4), ("head_bias", C.c_float * 4), ("head_lo", C.c_float * 4), ("head_hi", C.c_float * 4)]
 
 
 class RolloutDesc(C.Structure):
@@ -80,6 +88,20 @@ def load() -> C.CDLL:
     lib.mfb_lift_splat_backward.restype = C.c_int
     lib.mfb_conv_bn_act_bf16.argtypes = [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_void_p]
     lib.mfb_conv_bn_act_bf16.restype = C.c_int
+    lib.mfb_conv2d_bf16.argtypes = [C.POINTER(ConvDesc)] + [C.c_void_p] * 9
+    lib.mfb_conv2d_bf16.restype = C.c_int
+    lib.mfb_lift_splat_forward_bf16.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 8 + [C.c_void_p]
+    lib.mfb_lift_splat_forward_bf16.restype = C.c_int
+    lib.mfb_upsample_concat_nhwc_bf16.argtypes = [C.c_void_p] * 3 + [C.c_int] * 8 + [C.c_void_p]
+    lib.mfb_upsample_concat_nhwc_bf16.restype = C.c_int
+    lib.mfb_stem_conv_bf16.argtypes = [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]
+    lib.mfb_stem_conv_bf16.restype = C.c_int
+    lib.mfb_dwconv_bn_silu_bf16.argtypes = [C.c_void_p] * 5 + [C.c_int] * 10 + [C.c_void_p]
+    lib.mfb_dwconv_bn_silu_bf16.restype = C.c_int
+    lib.mfb_se_fold_bf16.argtypes = [C.c_void_p, C.c_float] + [C.c_void_p] * 6 + [C.c_int] * 5 + [C.c_void_p]
+    lib.mfb_se_fold_bf16.restype = C.c_int
+    lib.mfb_cast_f32_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
+    lib.mfb_cast_f32_to_bf16.restype = C.c_int
     lib.mfb_physics_loss.argtypes = ([C.c_void_p] * 4 + [C.c_int64] * 2 + [C.c_int] * 3 + [C.c_double, C.c_int] +
                                      [C.c_void_p] * 3 + [C.c_int, C.c_void_p])
     lib.mfb_physics_loss.restype = C.c_int

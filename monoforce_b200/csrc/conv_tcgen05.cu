@@ -1,4 +1,5 @@
 // Host side of K4 (conv_tcgen05.cuh): TMA tensor maps + launch, exported through the C ABI.
+#include <cstring>
 #include <mutex>
 #include <string>
 
@@ -35,7 +36,7 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p,
     const int smem = Smem<BLOCK_N>::kTotal;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return fail_status(MFB_ERR_CUDA, "conv: cudaFuncSetAttribute failed");
-    dim3 grid(p.tiles_w * p.tiles_h * p.N, p.Cout / BLOCK_N);
+    dim3 grid(p.tiles_w * p.tiles_h * p.N, (p.Cout + BLOCK_N - 1) / BLOCK_N);
     kern<<<grid, kThreads, smem, st>>>(mx, mw, p);
     count_launch();
     cudaError_t e = cudaGetLastError();
@@ -49,46 +50,85 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p,
 using namespace mfb;
 using namespace mfb::conv;
 
-extern "C" int mfb_conv_bn_act_bf16(const void* x, const void* wgt, const void* scale, const void* shift, void* y,
-                                    int N, int H, int W, int Cin, int Cout, int KS, int act, void* stream) {
-    if (!x || !wgt || !scale || !shift || !y) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: NULL pointer");
-    if (N < 1 || H < 1 || W < 1) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: sizes must be positive");
-    if (KS != 1 && KS != 3) return fail_status(MFB_ERR_UNSUPPORTED, "conv: kernel size must be 1 or 3");
-    if (Cin % kBlockK) return fail_status(MFB_ERR_UNSUPPORTED, "conv: Cin must be a multiple of 64 (pad the channels)");
-    if (Cout % 64) return fail_status(MFB_ERR_UNSUPPORTED, "conv: Cout must be a multiple of 64");
-    if (act < kNone || act > kGelu) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: unknown activation");
-    if (((uintptr_t)x | (uintptr_t)wgt | (uintptr_t)y) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: tensors must be 16-byte aligned");
+extern "C" int mfb_conv2d_bf16(const mfb_conv_desc* d, const void* x, const void* wgt, const void* scale, const void* shift,
+                               const void* residual, void* y, const void* head_w, void* head_out, void* stream) {
+    if (!d) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: desc is NULL");
+    if (!x || !wgt || !scale || !shift) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: NULL pointer");
+    const bool head = d->n_heads > 0;
+    if (head ? (!head_w || !head_out) : !y) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: output pointer is NULL");
+    if (d->N < 1 || d->H < 1 || d->W < 1 || d->Ho < 1 || d->Wo < 1) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: sizes must be positive");
+    if (d->KH < 1 || d->KH > 7 || d->KW < 1 || d->KW > 7) return fail_status(MFB_ERR_UNSUPPORTED, "conv: kernel size must be in [1, 7]");
+    if (d->stride != 1 && d->stride != 2) return fail_status(MFB_ERR_UNSUPPORTED, "conv: stride must be 1 or 2");
+    if (d->pad_h < 0 || d->pad_w < 0 || d->pad_h >= d->KH || d->pad_w >= d->KW) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: padding must be in [0, K)");
+    // every output pixel's window must start inside the zero-padded image
+    if ((d->Ho - 1) * d->stride - d->pad_h >= d->H || (d->Wo - 1) * d->stride - d->pad_w >= d->W)
+        return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: output size does not fit the input / stride / padding");
+    if (d->Cin < 8 || d->Cin % 8) return fail_status(MFB_ERR_UNSUPPORTED, "conv: Cin must be a multiple of 8 (16-byte rows for TMA)");
+    if (d->Cout < 8 || d->Cout % 8) return fail_status(MFB_ERR_UNSUPPORTED, "conv: Cout must be a multiple of 8");
+    if (d->act < kNone || d->act > kSilu) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: unknown activation");
+    if (((uintptr_t)x | (uintptr_t)wgt | (uintptr_t)y | (uintptr_t)residual) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: tensors must be 16-byte aligned");
+    const int block_n = d->Cout > 64 ? 128 : 64;
+    if (((uintptr_t)scale | (uintptr_t)shift) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: scale / shift must be 16-byte aligned");
+    if (head) {
+        if (d->n_heads > kMaxHeads || d->n_heads * block_n != d->Cout)
+            return fail_status(MFB_ERR_UNSUPPORTED, "conv: head mode needs Cout == n_heads * 128 (or 64) and n_heads <= 4");
+        if (residual) return fail_status(MFB_ERR_UNSUPPORTED, "conv: head mode takes no residual");
+        for (int i = 0; i < d->n_heads; ++i)
+            if (d->head_act[i] < kHeadNone || d->head_act[i] > kHeadScaledTanh) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: unknown head activation");
+    }
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail_status(MFB_ERR_CUDA, "conv: cuTensorMapEncodeTiled is not available from the driver");
 
-    const int block_n = (Cout % 128 == 0) ? 128 : 64;
+    const int N = d->N, H = d->H, W = d->W, Cin = d->Cin, Cout = d->Cout, st_ = d->stride;
     CUtensorMap mx, mw;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-        cuuint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
-        cuuint32_t es[4] = {1, 1, 1, 1};
+        // traversal strides: with stride s the box spans TW*s x TH*s input pixels and TMA keeps every s-th -> TW x TH rows
+        cuuint32_t box[4] = {kBlockK, (cuuint32_t)(kTileW * st_), (cuuint32_t)(kTileH * st_), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)st_, (cuuint32_t)st_, 1};
         CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail_status(MFB_ERR_CUDA, "conv: cuTensorMapEncodeTiled(x) failed with code " + std::to_string((int)r));
     }
     {
-        const cuuint64_t ktot = (cuuint64_t)KS * KS * Cin;
-        cuuint64_t dims[2] = {ktot, (cuuint64_t)Cout};
-        cuuint64_t strides[1] = {ktot * 2};
-        cuuint32_t box[2] = {kBlockK, (cuuint32_t)block_n};
-        cuuint32_t es[2] = {1, 1};
-        CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wgt), dims, strides, box, es,
+        const cuuint64_t ktot = (cuuint64_t)d->KH * d->KW * Cin;
+        const int rank = d->per_image_weights ? 3 : 2;
+        cuuint64_t dims[3] = {ktot, (cuuint64_t)Cout, (cuuint64_t)N};
+        cuuint64_t strides[2] = {ktot * 2, ktot * 2 * (cuuint64_t)Cout};
+        cuuint32_t box[3] = {kBlockK, (cuuint32_t)block_n, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(wgt), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail_status(MFB_ERR_CUDA, "conv: cuTensorMapEncodeTiled(w) failed with code " + std::to_string((int)r));
     }
     Params p;
-    p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KS = KS; p.act = act;
-    p.tiles_w = (W + kTileW - 1) / kTileW;
-    p.tiles_h = (H + kTileH - 1) / kTileH;
-    p.y = (__nv_bfloat16*)y; p.scale = (const float*)scale; p.shift = (const float*)shift;
+    p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Ho = d->Ho; p.Wo = d->Wo; p.Cout = Cout;
+    p.KH = d->KH; p.KW = d->KW; p.stride = st_; p.pad_h = d->pad_h; p.pad_w = d->pad_w; p.act = d->act;
+    p.tiles_w = (d->Wo + kTileW - 1) / kTileW;
+    p.tiles_h = (d->Ho + kTileH - 1) / kTileH;
+    p.per_image_w = d->per_image_weights ? 1 : 0;
+    p.y = (__nv_bfloat16*)y; p.res = (const __nv_bfloat16*)residual;
+    p.scale = (const float*)scale; p.shift = (const float*)shift;
+    p.head_out = head ? (float*)head_out : nullptr;
+    p.head_w = (const float*)head_w;
+    for (int i = 0; i < kMaxHeads; ++i) {
+        p.head_b[i] = d->head_bias[i]; p.head_lo[i] = d->head_lo[i]; p.head_hi[i] = d->head_hi[i]; p.head_act[i] = d->head_act[i];
+    }
     cudaStream_t st = (cudaStream_t)stream;
     return block_n == 128 ? launch<128>(mx, mw, p, st) : launch<64>(mx, mw, p, st);
+}
+
+// ABI v2 entry point: KS x KS, stride 1, "same" padding (kept for existing callers; forwards to mfb_conv2d_bf16)
+extern "C" int mfb_conv_bn_act_bf16(const void* x, const void* wgt, const void* scale, const void* shift, void* y,
+                                    int N, int H, int W, int Cin, int Cout, int KS, int act, void* stream) {
+    if (KS != 1 && KS != 3) return fail_status(MFB_ERR_UNSUPPORTED, "conv: kernel size must be 1 or 3");
+    if (act < kNone || act > kGelu) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: unknown activation");
+    mfb_conv_desc d;
+    memset(&d, 0, sizeof(d));
+    d.N = N; d.H = H; d.W = W; d.Cin = Cin; d.Ho = H; d.Wo = W; d.Cout = Cout;
+    d.KH = d.KW = KS; d.stride = 1; d.pad_h = d.pad_w = KS / 2; d.act = act;
+    return mfb_conv2d_bf16(&d, x, wgt, scale, shift, nullptr, y, nullptr, nullptr, stream);
 }

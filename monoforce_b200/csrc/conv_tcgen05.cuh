@@ -1,20 +1,26 @@
-// K4: dense KxK (K = 1 or 3), stride-1, "same"-padded convolution as an implicit GEMM on the 5th-gen tensor
-// cores (tcgen05.mma, accumulator in TMEM, operands staged by TMA), with the folded BatchNorm + activation
-// epilogue of the terrain encoder's dense layers:
-//     Up.conv (two 3x3 conv-BN-GELU)        terrain_encoder/lss.py:34-41
-//     BevEncode heads (3x3 conv-BN-GELU)    terrain_encoder/lss.py:117-139
-//     1x1 depthnet                          terrain_encoder/lss.py:58
+// K4: dense KH x KW convolution (stride 1 or 2, arbitrary low-side zero padding) as an implicit GEMM on the 5th-gen
+// tensor cores (tcgen05.mma, accumulator in TMEM, operands staged by TMA), with a fused epilogue.  It carries every
+// GEMM-shaped layer of the terrain encoder:
+//     Up.conv (two 3x3 conv-BN-GELU)                                   terrain_encoder/lss.py:34-41
+//     BevEncode conv1 7x7/2 + ResNet-18 layer1-3 (3x3, 3x3/2, 1x1/2,
+//       BN, residual add, ReLU)                                        terrain_encoder/lss.py:104-116,140-151
+//     BevEncode heads: 3x3 conv-BN-GELU + 1x1 conv + ScaledTanh/ReLU   terrain_encoder/lss.py:117-139
+//     1x1 depthnet                                                     terrain_encoder/lss.py:58
+//     EfficientNet-B0 MBConv 1x1 expand (BN+SiLU) / project (BN, skip) terrain_encoder/lss.py:73-94
 //
-//   y[n,h,w,co] = act( scale[co] * sum_{dy,dx,ci} x[n,h+dy-p,w+dx-p,ci] * wgt[co,dy,dx,ci] + shift[co] )
+//   t[n,h,w,co] = scale[co] * sum_{dy,dx,ci} x[n, s*h+dy-ph, s*w+dx-pw, ci] * wgt[(n,) co,dy,dx,ci] + shift[co]
+//   y = act(t + residual)                                   (bf16 NHWC), or, in head mode,
+//   out[n,g,h,w] = head_act_g( sum_{c < BLOCK_N} act(t)[g*BLOCK_N + c] * head_w[g*BLOCK_N + c] + head_b[g] )   (fp32)
 //
-// Layouts: x, y NHWC bf16; wgt [Cout][KS*KS*Cin] bf16 (K-major); scale / shift fp32.
+// Layouts: x, y, residual NHWC bf16; wgt [Cout][KH*KW*Cin] bf16 (K-major), optionally one matrix per image (the
+// squeeze-excite scale of an MBConv block folded into its projection weights); scale / shift fp32.
 // Tiling: one CTA = 128 output pixels (TH x TW = 8 x 16 patch of one image) x BLOCK_N output channels.
-// The K loop runs over (tap, 64-channel chunk): for each, TMA loads the SHIFTED activation patch as a 4-D box
-// {64 ch, TW, TH, 1} (out-of-image rows/columns are zero-filled by the TMA unit == the conv's zero padding) and
-// the matching weight slab {64, BLOCK_N}; both land in 128-byte-swizzled K-major shared tiles, the canonical
-// UMMA operand layout, so no im2col buffer ever exists.
+// The K loop runs over (tap, 64-channel chunk): for each, TMA loads the SHIFTED (and for stride 2: element-strided)
+// activation patch as a 4-D box {64 ch, TW*s, TH*s, 1} with traversal strides {1,s,s,1} (out-of-image rows/columns are
+// zero-filled by the TMA unit == the conv's zero padding) and the matching weight slab {64, BLOCK_N}; both land in
+// 128-byte-swizzled K-major shared tiles, the canonical UMMA operand layout, so no im2col buffer ever exists.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2-5 = epilogue (tcgen05.ld -> scale/shift/activation -> bf16 -> 16-byte global stores).
+// warps 2-5 = epilogue (tcgen05.ld -> scale/shift (+residual) -> activation -> bf16 16-byte stores | head dot product).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -31,14 +37,25 @@ constexpr int kBlockK = 64;       // bf16 channels per K chunk = one 128-byte sw
 constexpr int kStages = 3;       // 3 x 32 KB: two CTAs fit one SM, so one CTA's epilogue overlaps the other's MMAs
 constexpr int kThreads = 192;
 
-enum Act : int { kNone = 0, kRelu = 1, kGelu = 2 };
+enum Act : int { kNone = 0, kRelu = 1, kGelu = 2, kSilu = 3 };
+enum HeadAct : int { kHeadNone = 0, kHeadRelu = 1, kHeadScaledTanh = 2 };
+constexpr int kMaxHeads = 4;
 
 struct Params {
-    int N, H, W, Cin, Cout, KS, act;
+    int N, H, W, Cin;              // input  (N,H,W,Cin)
+    int Ho, Wo, Cout;              // output (N,Ho,Wo,Cout)
+    int KH, KW, stride, pad_h, pad_w, act;
     int tiles_w, tiles_h;
-    __nv_bfloat16* y;
+    int per_image_w;               // weights are (N, Cout, KH*KW*Cin): the CTA's image selects the matrix
+    __nv_bfloat16* y;              // nullptr in head mode
+    const __nv_bfloat16* res;      // residual added before the activation, or nullptr
     const float* scale;
     const float* shift;
+    // head mode: a 1x1 convolution to ONE channel per BLOCK_N-channel group + its output activation, fused
+    float* head_out;               // (N, Cout / BLOCK_N, Ho, Wo) fp32, or nullptr
+    const float* head_w;           // (Cout,)
+    float head_b[kMaxHeads], head_lo[kMaxHeads], head_hi[kMaxHeads];
+    int head_act[kMaxHeads];
 };
 
 template <int BLOCK_N>
@@ -75,6 +92,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  :: "r"(s_addr(dst)), "l"(map), "r"(s_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(s_addr(dst)), "l"(map), "r"(s_addr(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -129,6 +150,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == kRelu) return fmaxf(v, 0.f);
     if (act == kGelu) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));     // nn.GELU() (erf form)
+    if (act == kSilu) return __fdividef(v, 1.f + __expf(-v));                        // x * sigmoid(x)
     return v;
 }
 
@@ -151,9 +173,10 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     const int n = tile / (p.tiles_w * p.tiles_h);
     const int w0 = tw * kTileW, h0 = th * kTileH;
     const int n0 = blockIdx.y * BLOCK_N;
-    const int pad = p.KS / 2;
-    const int chunks_per_tap = p.Cin / kBlockK;
-    const int k_iters = p.KS * p.KS * chunks_per_tap;
+    // Cin need not be a multiple of 64: the last chunk's channels beyond Cin are outside the tensor map's extent, which the
+    // TMA unit fills with zeros (for the weights too, whose rows are KH*KW*Cin long), so they add nothing to the sum
+    const int chunks_per_tap = (p.Cin + kBlockK - 1) / kBlockK;
+    const int k_iters = p.KH * p.KW * chunks_per_tap;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_x) : "memory");
@@ -176,12 +199,15 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 const uint32_t round = i / kStages;
                 mbar_wait(empty + s, (round & 1) ^ 1);
                 const int tap = i / chunks_per_tap, c0 = (i - tap * chunks_per_tap) * kBlockK;
-                const int dy = tap / p.KS, dx = tap - dy * p.KS;
+                const int dy = tap / p.KW, dx = tap - dy * p.KW;
                 uint8_t* a_dst = smem + s * S::kStageBytes;
                 uint8_t* b_dst = a_dst + S::kABytes;
                 mbar_expect_tx(full + s, S::kStageBytes);
-                tma_load_4d(a_dst, &tmap_x, full + s, c0, w0 + dx - pad, h0 + dy - pad, n);
-                tma_load_2d(b_dst, &tmap_w, full + s, tap * p.Cin + c0, n0);
+                // input pixel of output (h, w) under tap (dy, dx): (stride*h + dy - pad_h, stride*w + dx - pad_w); the
+                // tensor map traverses W and H with step `stride`, so the box lands as TH x TW consecutive rows
+                tma_load_4d(a_dst, &tmap_x, full + s, c0, w0 * p.stride + dx - p.pad_w, h0 * p.stride + dy - p.pad_h, n);
+                if (p.per_image_w) tma_load_3d(b_dst, &tmap_w, full + s, tap * p.Cin + c0, n0, n);
+                else tma_load_2d(b_dst, &tmap_w, full + s, tap * p.Cin + c0, n0);
             }
         }
     } else if (warp == 1) {
@@ -213,25 +239,64 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         const int m = q * 32 + lane;                         // accumulator row == pixel inside the patch
         const int hh = m / kTileW, ww = m - hh * kTileW;
         const int h = h0 + hh, w = w0 + ww;
-        const bool in_image = (h < p.H) && (w < p.W);
-        __nv_bfloat16* out = p.y + (((long long)n * p.H + h) * p.W + w) * p.Cout + n0;
+        const bool in_image = (h < p.Ho) && (w < p.Wo);
+        const long long pix = ((long long)n * p.Ho + h) * p.Wo + w;
+        if (p.head_out != nullptr) {
+            // fused 1x1 head: one output channel per BLOCK_N-channel group (this CTA's group = blockIdx.y)
+            float dot = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
-            if (in_image) {
-                uint32_t packed[16];
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
+                for (int j = 0; j < 32; ++j) {
                     const int co = n0 + c + j;
-                    const float v0 = apply_act(__uint_as_float(r[j]) * __ldg(p.scale + co) + __ldg(p.shift + co), p.act);
-                    const float v1 = apply_act(__uint_as_float(r[j + 1]) * __ldg(p.scale + co + 1) + __ldg(p.shift + co + 1), p.act);
-                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
-                    packed[j >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+                    const float v = apply_act(__uint_as_float(r[j]) * __ldg(p.scale + co) + __ldg(p.shift + co), p.act);
+                    dot = fmaf(v, __ldg(p.head_w + co), dot);
                 }
-                uint4* dst = reinterpret_cast<uint4*>(out + c);
+            }
+            if (in_image) {
+                const int g = blockIdx.y;
+                float o = dot + p.head_b[g];
+                if (p.head_act[g] == kHeadRelu) o = fmaxf(o, 0.f);
+                else if (p.head_act[g] == kHeadScaledTanh) o = p.head_lo[g] + (p.head_hi[g] - p.head_lo[g]) * (tanhf(o) + 1.f) * 0.5f;
+                p.head_out[((long long)n * gridDim.y + g) * p.Ho * p.Wo + (long long)h * p.Wo + w] = o;
+            }
+        } else {
+            __nv_bfloat16* out = p.y + pix * p.Cout + n0;
+            const __nv_bfloat16* rsd = p.res ? p.res + pix * p.Cout + n0 : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
+                if (in_image) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        const int co = n0 + c + 8 * g8;
+                        if (co < p.Cout) {                    // Cout is a multiple of 8, not necessarily of BLOCK_N
+                            const float4 sc0 = __ldg(reinterpret_cast<const float4*>(p.scale + co)), sc1 = __ldg(reinterpret_cast<const float4*>(p.scale + co + 4));
+                            const float4 sh0 = __ldg(reinterpret_cast<const float4*>(p.shift + co)), sh1 = __ldg(reinterpret_cast<const float4*>(p.shift + co + 4));
+                            const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                            const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[8 * g8 + j]), sc[j], sh[j]);
+                            if (rsd) {
+                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rsd + c + 8 * g8));
+                                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(r2[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+                            }
+                            uint32_t pk[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const __nv_bfloat162 b2 = __floats2bfloat162_rn(apply_act(v[2 * j], p.act), apply_act(v[2 * j + 1], p.act));
+                                pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                            }
+                            *reinterpret_cast<uint4*>(out + c + 8 * g8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        }
+                    }
+                }
             }
         }
     }

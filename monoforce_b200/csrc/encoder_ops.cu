@@ -1,0 +1,354 @@
+// K7: the memory-bound pieces of the terrain encoder's inference path, NHWC bf16 end to end, so that nothing between the
+// tensor-core convolutions (K4, conv_tcgen05.cuh) goes back through NCHW / fp32 / framework ops.
+//
+//   upsample_concat   Up.forward: cat([skip, bilinear_up(x)], channel)                   terrain_encoder/lss.py:27-46
+//                     and the x2 nn.Upsample in front of every BEV head                  lss.py:117-139
+//   stem_conv         EfficientNet-B0 stem: 3x3/2 conv (TF "same" padding) + BN + swish  lss.py:78 (efficientnet_pytorch 0.7.1)
+//   dwconv            MBConv depthwise k x k conv + BN + swish, with the squeeze-excite
+//                     global average pool accumulated on the fly                        lss.py:83-90 (MBConvBlock.forward)
+//   se_fold           squeeze-excite MLP (reduce -> swish -> expand -> sigmoid) per image, folded into that image's copy
+//                     of the 1x1 projection matrix:  W_n[co,c] = W[co,c] * s_n[c]   (x * s) @ W^T == x @ W_n^T
+//   cast              fp32 -> bf16 (the lift-splat BEV grid is accumulated with fp32 atomics)
+//
+// All of them are HBM-bound: 16-byte vector loads / stores along the channel axis, fp32 arithmetic, one thread per
+// (pixel, 8-channel group).  Eval-mode BatchNorm is pre-folded by the host: weights carry the scale, `shift` the rest.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/monoforce_b200.h"
+
+namespace mfb {
+void count_launch();
+int fail_status(int code, const std::string& msg);
+
+namespace enc {
+
+struct alignas(16) Bf8 { __nv_bfloat162 v[4]; };
+
+__device__ __forceinline__ void unpack8(const Bf8& b, float* f) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(b.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ Bf8 pack8(const float* f) {
+    Bf8 b;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return b;
+}
+__device__ __forceinline__ Bf8 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const Bf8*>(p); }
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// out[n,h,w, 0:Cs] = skip[n,h,w,:];  out[n,h,w, Cs:Cs+Cl] = bilinear(low)[n,h,w,:] (align_corners=True);  rest = 0
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+upsample_concat_kernel(const __nv_bfloat16* __restrict__ skip, const __nv_bfloat16* __restrict__ low,
+                       __nv_bfloat16* __restrict__ out, int N, int H, int W, int Cs, int Hl, int Wl, int Cl, int Cout,
+                       float ry, float rx) {
+    const int G = Cout >> 3;
+    const long long total = (long long)N * H * W * G;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % G);
+        const long long pix = i / G;
+        const int w = (int)(pix % W);
+        const int h = (int)((pix / W) % H);
+        const int n = (int)(pix / ((long long)W * H));
+        const int c = g << 3;
+        Bf8 o;
+        if (c < Cs) {
+            o = ld8(skip + pix * Cs + c);
+        } else if (c < Cs + Cl) {
+            const int cl = c - Cs;
+            // torch upsample_bilinear2d, align_corners=True: src = dst * (in - 1) / (out - 1)
+            const float sy = ry * h, sx = rx * w;
+            const int y0 = min((int)sy, Hl - 1), x0 = min((int)sx, Wl - 1);
+            const int y1 = min(y0 + 1, Hl - 1), x1 = min(x0 + 1, Wl - 1);
+            const float ly = sy - y0, lx = sx - x0;
+            const __nv_bfloat16* base = low + (long long)n * Hl * Wl * Cl + cl;
+            float a[8], b[8], cc[8], d[8], r[8];
+            unpack8(ld8(base + ((long long)y0 * Wl + x0) * Cl), a);
+            unpack8(ld8(base + ((long long)y0 * Wl + x1) * Cl), b);
+            unpack8(ld8(base + ((long long)y1 * Wl + x0) * Cl), cc);
+            unpack8(ld8(base + ((long long)y1 * Wl + x1) * Cl), d);
+            const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = w00 * a[k] + w01 * b[k] + w10 * cc[k] + w11 * d[k];
+            o = pack8(r);
+        } else {
+            const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            o = pack8(z);
+        }
+        *reinterpret_cast<Bf8*>(out + pix * Cout + c) = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stem: img (N,3,H,W) fp32 NCHW -> y (N,Ho,Wo,32) bf16 NHWC; 3x3 stride 2, low-side padding (ph, pw); w (3,3,3,32) fp32
+// [dy][dx][ci][co] with BN scale folded; y = swish(conv + shift)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ shift,
+                 __nv_bfloat16* __restrict__ y, int N, int H, int W, int Ho, int Wo, int ph, int pw) {
+    __shared__ float ws[27 * 32];
+    __shared__ float sh[32];
+    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = w[i];
+    if (threadIdx.x < 32) sh[threadIdx.x] = shift[threadIdx.x];
+    __syncthreads();
+    const long long total = (long long)N * Ho * Wo;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
+        const int wo = (int)(pix % Wo);
+        const int ho = (int)((pix / Wo) % Ho);
+        const int n = (int)(pix / ((long long)Wo * Ho));
+        float acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = sh[c];
+        const float* base = img + (long long)n * 3 * H * W;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int hi = 2 * ho + dy - ph;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int wi = 2 * wo + dx - pw;
+                const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float v = ok ? __ldg(base + ((long long)ci * H + hi) * W + wi) : 0.f;
+                    const float* wr = ws + ((dy * 3 + dx) * 3 + ci) * 32;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = silu(acc[c]);
+        Bf8* dst = reinterpret_cast<Bf8*>(y + pix * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = pack8(acc + 8 * q);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// depthwise k x k conv + shift + swish; pool[n,c] += sum over this CTA's pixels of the output (fp32)
+// x (N,H,W,C), y (N,Ho,Wo,C) bf16; w (K*K, C) fp32 (BN scale folded); grid = (pixel-group tiles, N)
+// ---------------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
+              __nv_bfloat16* __restrict__ y, float* __restrict__ pool, int H, int W, int C, int Ho, int Wo, int stride,
+              int ph, int pw) {
+    extern __shared__ float pool_s[];                      // C partial sums of this CTA
+    const int n = blockIdx.y;
+    const int G = C >> 3;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) pool_s[i] = 0.f;
+    __syncthreads();
+    const long long per_img = (long long)Ho * Wo * G;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = (int)(i % G);
+    const int c = g << 3;
+    float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // what this thread adds to the pool
+    if (i < per_img) {
+        const int pix = (int)(i / G);
+        const int wo = pix % Wo, ho = pix / Wo;
+        float acc[8];
+        {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + c)), s1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
+            acc[0] = s0.x; acc[1] = s0.y; acc[2] = s0.z; acc[3] = s0.w; acc[4] = s1.x; acc[5] = s1.y; acc[6] = s1.z; acc[7] = s1.w;
+        }
+        const __nv_bfloat16* base = x + (long long)n * H * W * C + c;
+#pragma unroll
+        for (int dy = 0; dy < K; ++dy) {
+            const int hi = ho * stride + dy - ph;
+            if (hi < 0 || hi >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < K; ++dx) {
+                const int wi = wo * stride + dx - pw;
+                if (wi < 0 || wi >= W) continue;
+                float v[8];
+                unpack8(ld8(base + ((long long)hi * W + wi) * C), v);
+                const float* wr = w + (dy * K + dx) * C + c;
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr)), w1 = __ldg(reinterpret_cast<const float4*>(wr + 4));
+                acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
+                acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+                acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
+                acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = silu(acc[k]);
+        const Bf8 o = pack8(acc);
+        *reinterpret_cast<Bf8*>(y + ((long long)n * Ho * Wo + pix) * C + c) = o;
+        unpack8(o, r);                                         // the pool sees what the next layer sees: bf16-rounded values
+    }
+    if (pool) {
+        // lanes l and l + j*G of a warp hold the same channel group: fold them onto lane l < G first, so the shared-memory
+        // atomics below hit distinct addresses within a warp (the first MBConv blocks have only 4..18 channel groups)
+        const int lane = threadIdx.x & 31;
+        if (G < 32) {
+            float t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = r[k];
+            for (int src = lane + G; src - lane < 32; src += G) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float o = __shfl_sync(0xffffffffu, t[k], src & 31);
+                    if (src < 32) r[k] += o;
+                }
+            }
+        }
+        if (lane < G) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(pool_s + c + k, r[k]);
+        }
+    }
+    if (pool) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float v = pool_s[c];
+            if (v != 0.f) atomicAdd(pool + (long long)n * C + c, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// squeeze-excite folded into per-image projection weights.  grid = (ceil(Cout / kRows), N), 256 threads.
+//   m = pool[n,:] * inv_hw;  r = swish(Wr m + br)  (Sq);  s = sigmoid(We r + be)  (C);  out[n,co,c] = proj[co,c] * s[c]
+// Wr (Sq, Cse), We (Cse, Sq): Cse = the block's real channel count; channels [Cse, C) are padding: s = 0 there.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSeRows = 16;
+constexpr int kSeMaxC = 1280, kSeMaxSq = 64;
+__global__ void __launch_bounds__(256)
+se_fold_kernel(const float* __restrict__ pool, float inv_hw, const float* __restrict__ Wr, const float* __restrict__ br,
+               const float* __restrict__ We, const float* __restrict__ be, const __nv_bfloat16* __restrict__ proj,
+               __nv_bfloat16* __restrict__ out, int C, int Cse, int Sq, int Cout) {
+    __shared__ float m[kSeMaxC];
+    __shared__ float r[kSeMaxSq];
+    __shared__ float s[kSeMaxC];
+    const int n = blockIdx.y;
+    for (int c = threadIdx.x; c < Cse; c += blockDim.x) m[c] = pool[(long long)n * C + c] * inv_hw;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int q = warp; q < Sq; q += 8) {
+        float a = 0.f;
+        for (int c = lane; c < Cse; c += 32) a = fmaf(__ldg(Wr + (long long)q * Cse + c), m[c], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) r[q] = silu(a + __ldg(br + q));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float v = 0.f;
+        if (c < Cse) {
+            float a = __ldg(be + c);
+            for (int q = 0; q < Sq; ++q) a = fmaf(__ldg(We + (long long)c * Sq + q), r[q], a);
+            v = __fdividef(1.f, 1.f + __expf(-a));
+        }
+        s[c] = v;
+    }
+    __syncthreads();
+    const int row0 = blockIdx.x * kSeRows;
+    const int G = C >> 3;
+    for (int i = threadIdx.x; i < kSeRows * G; i += blockDim.x) {
+        const int row = row0 + i / G, c = (i % G) << 3;
+        if (row >= Cout) break;
+        float v[8];
+        unpack8(ld8(proj + (long long)row * C + c), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] *= s[c + k];
+        *reinterpret_cast<Bf8*>(out + ((long long)n * Cout + row) * C + c) = pack8(v);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+cast_kernel(const float4* __restrict__ src, Bf8* __restrict__ dst, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(src + 2 * i), b = __ldg(src + 2 * i + 1);
+        const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        dst[i] = pack8(f);
+    }
+}
+
+static int after_launch(const char* what) {
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_status(MFB_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+    return MFB_OK;
+}
+static unsigned grid_for(long long work, int block, int max_ctas = 148 * 16) {
+    long long g = (work + block - 1) / block;
+    return (unsigned)(g < 1 ? 1 : (g > max_ctas ? max_ctas : g));
+}
+
+}  // namespace enc
+}  // namespace mfb
+
+using namespace mfb;
+using namespace mfb::enc;
+
+extern "C" {
+
+int mfb_upsample_concat_nhwc_bf16(const void* skip, const void* low, void* out, int N, int H, int W, int C_skip, int Hl,
+                                  int Wl, int C_low, int C_out, void* stream) {
+    if (!low || !out || (C_skip > 0 && !skip)) return fail_status(MFB_ERR_INVALID_ARGUMENT, "upsample_concat: NULL pointer");
+    if (N < 1 || H < 1 || W < 1 || Hl < 1 || Wl < 1) return fail_status(MFB_ERR_INVALID_ARGUMENT, "upsample_concat: sizes must be positive");
+    if ((C_skip | C_low | C_out) & 7 || C_low < 8 || C_skip < 0 || C_out < C_skip + C_low)
+        return fail_status(MFB_ERR_UNSUPPORTED, "upsample_concat: channel counts must be multiples of 8 and C_out >= C_skip + C_low");
+    if (((uintptr_t)skip | (uintptr_t)low | (uintptr_t)out) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "upsample_concat: tensors must be 16-byte aligned");
+    const float ry = H > 1 ? (float)(Hl - 1) / (float)(H - 1) : 0.f, rx = W > 1 ? (float)(Wl - 1) / (float)(W - 1) : 0.f;
+    const long long total = (long long)N * H * W * (C_out >> 3);
+    upsample_concat_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)skip, (const __nv_bfloat16*)low, (__nv_bfloat16*)out, N, H, W, C_skip, Hl, Wl, C_low, C_out, ry, rx);
+    return after_launch("upsample_concat");
+}
+
+int mfb_stem_conv_bf16(const void* img, const void* w, const void* shift, void* y, int N, int H, int W, int Ho, int Wo,
+                       int pad_h, int pad_w, void* stream) {
+    if (!img || !w || !shift || !y) return fail_status(MFB_ERR_INVALID_ARGUMENT, "stem_conv: NULL pointer");
+    if (N < 1 || H < 1 || W < 1 || Ho < 1 || Wo < 1) return fail_status(MFB_ERR_INVALID_ARGUMENT, "stem_conv: sizes must be positive");
+    if (2 * (Ho - 1) - pad_h >= H || 2 * (Wo - 1) - pad_w >= W) return fail_status(MFB_ERR_INVALID_ARGUMENT, "stem_conv: output size does not fit");
+    const long long total = (long long)N * Ho * Wo;
+    stem_conv_kernel<<<grid_for(total, 128, 148 * 16), 128, 0, (cudaStream_t)stream>>>(
+        (const float*)img, (const float*)w, (const float*)shift, (__nv_bfloat16*)y, N, H, W, Ho, Wo, pad_h, pad_w);
+    return after_launch("stem_conv");
+}
+
+int mfb_dwconv_bn_silu_bf16(const void* x, const void* w, const void* shift, void* y, void* pool, int N, int H, int W, int C,
+                            int Ho, int Wo, int K, int stride, int pad_h, int pad_w, void* stream) {
+    if (!x || !w || !shift || !y) return fail_status(MFB_ERR_INVALID_ARGUMENT, "dwconv: NULL pointer");
+    if (N < 1 || H < 1 || W < 1 || Ho < 1 || Wo < 1) return fail_status(MFB_ERR_INVALID_ARGUMENT, "dwconv: sizes must be positive");
+    if (C & 7 || C < 8 || C > 12288) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: C must be a multiple of 8");
+    if (K != 3 && K != 5) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: kernel size must be 3 or 5");
+    if (stride != 1 && stride != 2) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: stride must be 1 or 2");
+    if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)w | (uintptr_t)shift) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "dwconv: tensors must be 16-byte aligned");
+    const long long per_img = (long long)Ho * Wo * (C >> 3);
+    dim3 grid((unsigned)((per_img + 255) / 256), (unsigned)N);
+    const size_t smem = (size_t)C * sizeof(float);
+    auto args = [&](auto kern) {
+        kern<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const float*)w, (const float*)shift,
+                                                        (__nv_bfloat16*)y, (float*)pool, H, W, C, Ho, Wo, stride, pad_h, pad_w);
+    };
+    if (K == 3) args(dwconv_kernel<3>); else args(dwconv_kernel<5>);
+    return after_launch("dwconv");
+}
+
+int mfb_se_fold_bf16(const void* pool, float inv_hw, const void* w_reduce, const void* b_reduce, const void* w_expand,
+                     const void* b_expand, const void* proj_w, void* out_w, int N, int C, int C_se, int Sq, int Cout, void* stream) {
+    if (!pool || !w_reduce || !b_reduce || !w_expand || !b_expand || !proj_w || !out_w) return fail_status(MFB_ERR_INVALID_ARGUMENT, "se_fold: NULL pointer");
+    if (N < 1 || Cout < 1 || Sq < 1 || Sq > kSeMaxSq || C < 8 || C > kSeMaxC || (C & 7) || C_se < 1 || C_se > C)
+        return fail_status(MFB_ERR_UNSUPPORTED, "se_fold: need C % 8 == 0, C <= 1280, Sq <= 64, C_se <= C");
+    dim3 grid((unsigned)((Cout + kSeRows - 1) / kSeRows), (unsigned)N);
+    se_fold_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)pool, inv_hw, (const float*)w_reduce, (const float*)b_reduce,
+                                                           (const float*)w_expand, (const float*)b_expand, (const __nv_bfloat16*)proj_w,
+                                                           (__nv_bfloat16*)out_w, C, C_se, Sq, Cout);
+    return after_launch("se_fold");
+}
+
+int mfb_cast_f32_to_bf16(const void* src, void* dst, long long n, void* stream) {
+    if (!src || !dst) return fail_status(MFB_ERR_INVALID_ARGUMENT, "cast: NULL pointer");
+    if (n < 8 || (n & 7) || (((uintptr_t)src | (uintptr_t)dst) & 15)) return fail_status(MFB_ERR_UNSUPPORTED, "cast: n must be a multiple of 8, pointers 16-byte aligned");
+    cast_kernel<<<grid_for(n >> 3, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>((const float4*)src, (Bf8*)dst, n >> 3);
+    return after_launch("cast");
+}
+
+}  // extern "C"

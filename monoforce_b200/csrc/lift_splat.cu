@@ -9,6 +9,7 @@
 // falls inside the grid the warp adds depth_d * feats to the channels-last BEV cell with ONE coalesced 256-byte
 // vector reduction (red.global.add.v2.f32).  The lifted tensor and the argsort never exist.
 // Backward is the matching gather: no atomics.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -33,12 +34,16 @@ __device__ __forceinline__ float wsum(float v) {
     return v;
 }
 
-// logits: (B*N*fH*fW, D + 64) channels-last rows;  vox: (B*N, D, fH, fW) flat BEV cell or -1
-template <bool BACKWARD>
+__device__ __forceinline__ float ldv(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldv(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// logits: (B*N*fH*fW) channels-last rows of `row_stride` scalars, the first D + 64 are used (fp32, or bf16 straight from the
+// tensor-core depthnet whose output rows are padded to 128 channels);  vox: (B*N, D, fH, fW) flat BEV cell or -1
+template <bool BACKWARD, typename LT>
 __global__ void __launch_bounds__(256)
-lift_splat_kernel(const float* __restrict__ logits, const int* __restrict__ vox, float* __restrict__ bev,
+lift_splat_kernel(const LT* __restrict__ logits, const int* __restrict__ vox, float* __restrict__ bev,
                   const float* __restrict__ g_bev, float* __restrict__ g_logits,
-                  int B, int N, int D, int fH, int fW, int XY) {
+                  int B, int N, int D, int fH, int fW, int XY, int row_stride) {
     constexpr int C = 64;
     const int lane = threadIdx.x & 31;
     const long long n_pix = (long long)B * N * fH * fW;
@@ -48,7 +53,7 @@ lift_splat_kernel(const float* __restrict__ logits, const int* __restrict__ vox,
     const long long bn = pix / hw;
     const int p_hw = (int)(pix - bn * hw);
     const int b = (int)(bn / N);
-    const float* row = logits + pix * (D + C);
+    const LT* row = logits + pix * row_stride;
 
     // depth soft-max (lss.py:60-61,68): lane l owns depth bins l, l+32, ...
     float lg[kMaxDepthSlots], dep[kMaxDepthSlots];
@@ -57,7 +62,7 @@ lift_splat_kernel(const float* __restrict__ logits, const int* __restrict__ vox,
 #pragma unroll
     for (int s = 0; s < kMaxDepthSlots; ++s) {
         const int d = s * 32 + lane;
-        lg[s] = d < D ? __ldg(row + d) : -INFINITY;
+        lg[s] = d < D ? ldv(row + d) : -INFINITY;
         vx[s] = d < D ? __ldg(vox + (bn * D + d) * hw + p_hw) : -1;
         m = fmaxf(m, lg[s]);
     }
@@ -71,7 +76,7 @@ lift_splat_kernel(const float* __restrict__ logits, const int* __restrict__ vox,
     for (int s = 0; s < kMaxDepthSlots; ++s) dep[s] *= inv;
 
     // channels 2l, 2l+1 (scalar loads: a row is D + 64 floats and D may be odd, e.g. 59)
-    const float2 f = make_float2(__ldg(row + D + 2 * lane), __ldg(row + D + 2 * lane + 1));
+    const float2 f = make_float2(ldv(row + D + 2 * lane), ldv(row + D + 2 * lane + 1));
 
     if (!BACKWARD) {
         float* cellbase = bev + (long long)b * XY * C + 2 * lane;
@@ -137,11 +142,26 @@ int mfb_lift_splat_forward(const void* logits, const void* vox, void* bev, int B
     if (!logits || !vox || !bev) return fail_status(MFB_ERR_INVALID_ARGUMENT, "NULL pointer");
     const long long n_pix = (long long)B * N * fH * fW;
     const int wpb = 8;
-    lift_splat_kernel<false><<<(unsigned)((n_pix + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-        (const float*)logits, (const int*)vox, (float*)bev, nullptr, nullptr, B, N, D, fH, fW, X * Y);
+    lift_splat_kernel<false, float><<<(unsigned)((n_pix + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const float*)logits, (const int*)vox, (float*)bev, nullptr, nullptr, B, N, D, fH, fW, X * Y, D + C);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_status(MFB_ERR_CUDA, std::string("lift_splat forward launch: ") + cudaGetErrorString(e));
+    return MFB_OK;
+}
+
+int mfb_lift_splat_forward_bf16(const void* logits, int row_stride, const void* vox, void* bev, int B, int N, int D, int C,
+                                int fH, int fW, int X, int Y, void* stream) {
+    if (const char* m = check(B, N, D, C, fH, fW, X, Y)) return fail_status(MFB_ERR_INVALID_ARGUMENT, m);
+    if (!logits || !vox || !bev) return fail_status(MFB_ERR_INVALID_ARGUMENT, "NULL pointer");
+    if (row_stride < D + C) return fail_status(MFB_ERR_INVALID_ARGUMENT, "row_stride must be >= D + C");
+    const long long n_pix = (long long)B * N * fH * fW;
+    const int wpb = 8;
+    lift_splat_kernel<false, __nv_bfloat16><<<(unsigned)((n_pix + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)logits, (const int*)vox, (float*)bev, nullptr, nullptr, B, N, D, fH, fW, X * Y, row_stride);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_status(MFB_ERR_CUDA, std::string("lift_splat forward (bf16) launch: ") + cudaGetErrorString(e));
     return MFB_OK;
 }
 
@@ -151,8 +171,8 @@ int mfb_lift_splat_backward(const void* logits, const void* vox, const void* g_b
     if (!logits || !vox || !g_bev || !g_logits) return fail_status(MFB_ERR_INVALID_ARGUMENT, "NULL pointer");
     const long long n_pix = (long long)B * N * fH * fW;
     const int wpb = 8;
-    lift_splat_kernel<true><<<(unsigned)((n_pix + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-        (const float*)logits, (const int*)vox, nullptr, (const float*)g_bev, (float*)g_logits, B, N, D, fH, fW, X * Y);
+    lift_splat_kernel<true, float><<<(unsigned)((n_pix + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        (const float*)logits, (const int*)vox, nullptr, (const float*)g_bev, (float*)g_logits, B, N, D, fH, fW, X * Y, D + C);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_status(MFB_ERR_CUDA, std::string("lift_splat backward launch: ") + cudaGetErrorString(e));

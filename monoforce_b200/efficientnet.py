@@ -76,34 +76,9 @@ def drop_connect(x, p, training):
     return x / keep * mask
 
 
-def fold_conv_bn_nchw(conv: nn.Conv2d, bn: nn.BatchNorm2d | None, dtype):
-    """Eval-mode BatchNorm folded into the preceding convolution: (weight, bias) in `dtype`, weight channels-last.
-
-    y = gamma (conv(x) - mean) / sqrt(var + eps) + beta  ==  conv(x, w * s) + (beta - mean * s),  s = gamma / sqrt(var + eps)."""
-    w = conv.weight.detach().float()
-    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
-    if bn is not None:
-        s = bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)
-        w = w * s.view(-1, 1, 1, 1)
-        b = bn.bias.detach().float() + (b - bn.running_mean.detach().float()) * s
-    return w.to(dtype).contiguous(memory_format=torch.channels_last), b.to(dtype)
-
-
 def params_stamp(module: nn.Module):
     """Cheap fingerprint of a module's parameters / buffers: storage addresses + in-place version counters."""
     return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
-
-
-def _conv_same(x, conv: "Conv2dStaticSamePadding", w, b):
-    """The static-same-padded convolution with folded (w, b): symmetric padding goes into the conv call (no pad copy),
-    only the asymmetric stride-2 cases need an explicit F.pad."""
-    pad = conv.static_padding
-    if isinstance(pad, nn.ZeroPad2d):
-        l, r, t, bt = pad.padding
-        if l == r and t == bt:
-            return F.conv2d(x, w, b, conv.stride, (t, l), conv.dilation, conv.groups)
-        x = F.pad(x, (l, r, t, bt))
-    return F.conv2d(x, w, b, conv.stride, 0, conv.dilation, conv.groups)
 
 
 class MBConvBlock(nn.Module):
@@ -143,67 +118,8 @@ class MBConvBlock(nn.Module):
         return x
 
 
-def _mbconv_fast(block: "MBConvBlock", x, f):
-    """Eval-mode MBConv on folded weights `f` (see EfficientNet.folded): conv+bias, one fused SiLU per activation."""
-    a = block._block_args
-    inputs = x
-    if a.expand_ratio != 1:
-        x = F.silu(_conv_same(x, block._expand_conv, *f["expand"]))
-    x = F.silu(_conv_same(x, block._depthwise_conv, *f["dw"]))
-    s = x.mean((2, 3), keepdim=True)
-    s = F.conv2d(F.silu(F.conv2d(s, *f["se_r"])), *f["se_e"])
-    x = torch.sigmoid(s) * x
-    x = _conv_same(x, block._project_conv, *f["proj"])
-    if a.id_skip and a.stride == 1 and a.input_filters == a.output_filters:
-        x = x + inputs
-    return x
-
-
 class EfficientNet(nn.Module):
     """`EfficientNet.from_name('efficientnet-b0')` of efficientnet_pytorch, trunk + (unused) head."""
-
-    def folded(self, dtype):
-        """Eval-mode inference weights: every BatchNorm folded into its convolution (built once, cached on the module;
-        the cache is dropped by train() / eval())."""
-        key = "_mfb_folded_" + str(dtype)
-        cache = self.__dict__.get(key)
-        stamp = params_stamp(self)            # in-place weight updates (optimizer step, load_state_dict) invalidate the fold
-        if cache is not None and cache["stamp"] != stamp:
-            cache = None
-        if cache is None:
-            with torch.no_grad():
-                blocks = []
-                for blk in self._blocks:
-                    f = {"dw": fold_conv_bn_nchw(blk._depthwise_conv, blk._bn1, dtype),
-                         "se_r": fold_conv_bn_nchw(blk._se_reduce, None, dtype),
-                         "se_e": fold_conv_bn_nchw(blk._se_expand, None, dtype),
-                         "proj": fold_conv_bn_nchw(blk._project_conv, blk._bn2, dtype)}
-                    if blk._block_args.expand_ratio != 1:
-                        f["expand"] = fold_conv_bn_nchw(blk._expand_conv, blk._bn0, dtype)
-                    blocks.append(f)
-                cache = {"stem": fold_conv_bn_nchw(self._conv_stem, self._bn0, dtype), "blocks": blocks, "stamp": stamp}
-            self.__dict__[key] = cache
-        return cache
-
-    def train(self, mode: bool = True):
-        for k in [k for k in self.__dict__ if k.startswith("_mfb_folded_")]:
-            del self.__dict__[k]
-        return super().train(mode)
-
-    def fast_endpoints(self, x, dtype=torch.bfloat16):
-        """Eval-mode trunk on folded weights in `dtype`, channels-last: the feature map before every down-sampling plus
-        the last one (what `CamEncode.get_eff_depth` collects, lss.py:73-94)."""
-        f = self.folded(dtype)
-        x = x.to(dtype).contiguous(memory_format=torch.channels_last)
-        x = F.silu(_conv_same(x, self._conv_stem, *f["stem"]))
-        feats, prev = [], x
-        for blk, fb in zip(self._blocks, f["blocks"]):
-            x = _mbconv_fast(blk, x, fb)
-            if prev.size(2) > x.size(2):
-                feats.append(prev)
-            prev = x
-        feats.append(x)
-        return feats
 
     def __init__(self, blocks_args=None, global_params=None, in_channels=3):
         super().__init__()

@@ -11,10 +11,12 @@ What runs where:
     (csrc/lift_splat.cu): per frustum pixel, depth soft-max in registers, then depth-weighted features
     are scatter-added straight into the channels-last BEV grid.  The (B,N,C,D,fH,fW) lifted tensor
     (395 MB at B=16) and the argsort are never materialised.  Backward is a gather kernel.
-  * dense convolutions go through torch (cuDNN) in fp32 by default, which is the parity path.  With
-    `net.fast_inference = True` (eval mode only) the GEMM-shaped layers - `Up` blocks, the 1x1 `depthnet`,
-    the three BEV heads - run as bf16 implicit GEMMs on the tcgen05 tensor cores with eval-mode BatchNorm and
-    the activation fused into the epilogue (csrc/conv_tcgen05.cuh); depthwise / strided convs stay on cuDNN.
+  * the module path (training, or eval with gradients) runs the convolutions through torch in fp32: that is the parity
+    path against the reference.  With `net.fast_inference = True` (eval mode, no_grad) the WHOLE network runs on repo
+    kernels in NHWC bf16 (monoforce_b200/encoder_fast.py): every dense convolution - EfficientNet 1x1 expand / project,
+    `Up` blocks, depthnet, conv1 7x7/2, ResNet-18 layer1-3, the heads incl. their 1x1 outputs - as implicit GEMMs on the
+    tcgen05 tensor cores (csrc/conv_tcgen05.cuh), the depthwise / squeeze-excite / upsample / stem layers as fused
+    memory-bound kernels (csrc/encoder_ops.cu).
 The frustum geometry (`get_geometry`, lss.py:204-224) is a handful of tiny 3x3 ops kept in torch.
 """
 from __future__ import annotations
@@ -28,7 +30,7 @@ from torch.nn import functional as F
 from torchvision.models.resnet import resnet18
 
 from . import _lib, ops
-from .efficientnet import EfficientNet, fold_conv_bn_nchw, params_stamp
+from .efficientnet import EfficientNet
 
 _H_MAX = 2.0      # DPhysConfig().h_max, the default range of ScaledTanh (lss.py:15-19)
 
@@ -67,55 +69,6 @@ class Up(nn.Module):
 
     def forward(self, x1, x2):
         return self.conv(torch.cat([x2, self.up(x1)], dim=1))
-
-    def fast_nhwc(self, x1, x2):
-        """Inference path: NCHW in (any float dtype; bf16 channels-last inputs are used as they are), NHWC bf16 out, both
-        conv-BN-GELU triples on the tensor cores."""
-        f = _folded(self, lambda: [ops.fold_conv_bn(self.conv[0], self.conv[1]), ops.fold_conv_bn(self.conv[3], self.conv[4])])
-        x = _cat_up_nhwc_bf16(self.up, x1, x2, f[0][0].shape[-1])
-        x = ops.conv_bn_act_nhwc(x, *f[0], ops.ACT_GELU)
-        return ops.conv_bn_act_nhwc(x, *f[1], ops.ACT_GELU)
-
-
-def _cat_up_nhwc_bf16(up, x1, x2, c_padded):
-    """cat([x2, up(x1)], channel) written straight into one (N,H,W,c_padded) bf16 buffer: the up-sampling runs in bf16
-    channels-last and the concatenation / layout change / zero padding are two strided copies, instead of the fp32
-    up-sample + cat + convert passes."""
-    x1 = x1.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    u = up(x1)
-    N, C2, H, W = x2.shape
-    C1 = u.shape[1]
-    assert u.shape[2:] == x2.shape[2:] and C1 + C2 <= c_padded
-    out = torch.empty(N, H, W, c_padded, dtype=torch.bfloat16, device=x2.device)
-    out[..., :C2] = x2.permute(0, 2, 3, 1)
-    out[..., C2:C2 + C1] = u.permute(0, 2, 3, 1)
-    if C1 + C2 < c_padded:
-        out[..., C1 + C2:] = 0
-    return out
-
-
-def _to_nhwc_bf16(x, c_padded):
-    """(N,C,H,W) float -> (N,H,W,c_padded) bf16 with zero channel padding."""
-    N, Cc, H, W = x.shape
-    if Cc == c_padded:
-        return x.permute(0, 2, 3, 1).to(torch.bfloat16).contiguous()
-    out = torch.zeros(N, H, W, c_padded, dtype=torch.bfloat16, device=x.device)
-    out[..., :Cc] = x.permute(0, 2, 3, 1)
-    return out
-
-
-def _folded(module, build):
-    """Per-module cache of folded (weights, scale, shift), keyed on `params_stamp(module)`: storage addresses + in-place
-    version counters of every parameter / buffer, so load_state_dict / from_pretrained / an optimizer step invalidate
-    it (as EfficientNet.folded and BevEncode.fast_backbone_endpoints do)."""
-    stamp = params_stamp(module)
-    cache = module.__dict__.get("_mfb_folded")
-    if cache is None or cache[0] != stamp:
-        with torch.no_grad():
-            cache = (stamp, build())
-        module.__dict__["_mfb_folded"] = cache
-    return cache[1]
-
 
 class CamEncode(nn.Module):
     """EfficientNet-B0 trunk -> Up(320+112 -> 512) -> 1x1 `depthnet` giving D depth logits + C features
@@ -157,18 +110,6 @@ class CamEncode(nn.Module):
     def depth_logits_and_feats(self, x):
         return self.depthnet(self.get_eff_depth(x))
 
-    def fast_logits_nhwc(self, x):
-        """Inference path: (BN, fH, fW, D + C) fp32 rows for the lift-splat kernel; `up1` and `depthnet` on tcgen05."""
-        t = self.trunk
-        # the trunk's depthwise / squeeze-excite / strided layers are memory-bound, not GEMM-shaped: they stay on
-        # cuDNN, in bf16 channels-last (half the bytes per activation pass) with every BatchNorm folded into its
-        # convolution and one fused SiLU per activation (no separate BN / sigmoid / mul / pad passes)
-        feats = t.fast_endpoints(x)
-        y = self.up1.fast_nhwc(feats[4], feats[3])                           # (BN, fH, fW, 512) bf16
-        f = _folded(self, lambda: _fold_padded_cout(self.depthnet))
-        logits = ops.conv_bn_act_nhwc(y, *f, ops.ACT_NONE)                    # (BN, fH, fW, 128) bf16, 123 used
-        return logits[..., :self.D + self.C].float().contiguous()
-
     def get_depth_feat(self, x):
         x = self.depth_logits_and_feats(x)
         depth = self.get_depth_dist(x[:, :self.D])
@@ -176,17 +117,6 @@ class CamEncode(nn.Module):
 
     def forward(self, x):
         return self.get_depth_feat(x)[1]
-
-
-def _fold_padded_cout(conv, multiple=64):
-    """1x1 conv whose Cout is not a multiple of 64 (depthnet: D + C = 123): zero-pad the output channels."""
-    w, scale, shift = ops.fold_conv_bn(conv, None)
-    Cout = w.shape[0]
-    cp = (Cout + multiple - 1) // multiple * multiple
-    wp = torch.zeros(cp, *w.shape[1:], dtype=w.dtype, device=w.device)
-    wp[:Cout] = w
-    pad = lambda v, fill: torch.cat([v, torch.full((cp - Cout,), fill, device=v.device)])
-    return wp.contiguous(), pad(scale, 1.0), pad(shift, 0.0)
 
 
 def _head(outC, act):
@@ -217,49 +147,6 @@ class BevEncode(nn.Module):
         x = self.backbone(x)
         geom, diff, friction = self.up_geom(x), self.up_diff(x), self.up_friction(x)
         return {'geom': geom, 'terrain': geom - diff, 'diff': diff, 'friction': friction}
-
-    def fast_backbone_endpoints(self, x, dtype=torch.bfloat16):
-        """Eval-mode ResNet-18 stem + layer1..3 (lss.py:104-116) with every BatchNorm folded into its convolution, in
-        `dtype` channels-last: returns (layer1 output, layer3 output)."""
-        stamp = params_stamp(self)
-        cache = self.__dict__.get("_mfb_resnet_folded")
-        if cache is None or cache["stamp"] != stamp or cache["dtype"] != dtype:
-            with torch.no_grad():
-                layers = []
-                for layer in (self.layer1, self.layer2, self.layer3):
-                    for blk in layer:
-                        ds = fold_conv_bn_nchw(blk.downsample[0], blk.downsample[1], dtype) if blk.downsample is not None else None
-                        layers.append((blk, fold_conv_bn_nchw(blk.conv1, blk.bn1, dtype), fold_conv_bn_nchw(blk.conv2, blk.bn2, dtype), ds))
-                cache = {"stamp": stamp, "dtype": dtype, "stem": fold_conv_bn_nchw(self.conv1, self.bn1, dtype), "layers": layers}
-            self.__dict__["_mfb_resnet_folded"] = cache
-        conv = lambda t, c, wb: F.conv2d(t, wb[0], wb[1], c.stride, c.padding, c.dilation, c.groups)
-        x = x.to(dtype).contiguous(memory_format=torch.channels_last)
-        x = F.relu(conv(x, self.conv1, cache["stem"]))
-        x1 = None
-        n1 = len(self.layer1)
-        for i, (blk, f1, f2, ds) in enumerate(cache["layers"]):
-            idt = x if ds is None else conv(x, blk.downsample[0], ds)
-            x = F.relu(conv(F.relu(conv(x, blk.conv1, f1)), blk.conv2, f2).add_(idt))
-            if i == n1 - 1:
-                x1 = x
-        return x1, x
-
-    def fast_forward(self, x):
-        """Inference path: `up1` and the three head convs (one fused 256 -> 3x128 launch) on tcgen05."""
-        x1, x3 = self.fast_backbone_endpoints(x)                             # strided ResNet layers: cuDNN bf16 channels-last
-        y = self.up1.fast_nhwc(x3, x1)                                        # (B, X/2, Y/2, 256) bf16
-        heads = (self.up_geom, self.up_diff, self.up_friction)
-
-        def build():
-            parts = [ops.fold_conv_bn(h[1], h[2]) for h in heads]
-            return [torch.cat([p[i] for p in parts]).contiguous() for i in range(3)]
-        f = _folded(self, build)
-        up = heads[0][0](y.permute(0, 3, 1, 2))                               # shared x2 bilinear up-sampling, bf16 channels-last
-        z = ops.conv_bn_act_nhwc(_to_nhwc_bf16(up, 256), *f, ops.ACT_GELU)    # (B, X, Y, 384)
-        z = z.permute(0, 3, 1, 2).float()
-        geom, diff, friction = (h[5](h[4](z[:, 128 * i:128 * (i + 1)])) for i, h in enumerate(heads))
-        return {'geom': geom, 'terrain': geom - diff, 'diff': diff, 'friction': friction}
-
 
 # ---------------------------------------------------------------------------------------------
 # fused lift + splat
@@ -317,11 +204,6 @@ class LiftSplatShoot(nn.Module):
         self.bevencode = BevEncode(inC=self.camC, outC=outC)
         self.use_quickcumsum = True      # kept for attribute compatibility; the fused kernel needs neither path
         self.fast_inference = False      # opt-in: bf16 tcgen05 path for the dense layers (eval mode only)
-
-    def train(self, mode=True):
-        for m in self.modules():         # folded inference weights are stale once parameters may change
-            m.__dict__.pop("_mfb_folded", None)
-        return super().train(mode)
 
     def create_frustum(self):
         """(D, fH, fW, 3) image-plane sample points (u, v, depth) - lss.py:188-202."""
@@ -392,10 +274,7 @@ class LiftSplatShoot(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("monoforce_b200.LiftSplatShoot runs on CUDA only (fused lift-splat kernel, no CPU fallback)")
         vox = self.cached_voxel_index(rots, trans, intrins, post_rots, post_trans)
-        if self._fast():
-            logits = self.camencode.fast_logits_nhwc(x.view(B * N, Cin, H, W))
-        else:
-            logits = self.camencode.depth_logits_and_feats(x.view(B * N, Cin, H, W)).float().permute(0, 2, 3, 1)
+        logits = self.camencode.depth_logits_and_feats(x.view(B * N, Cin, H, W)).float().permute(0, 2, 3, 1)
         X, Y = int(self.nx[0]), int(self.nx[1])
         bev = _LiftSplat.apply(logits, vox.view(-1), B, N, self.D, self.camC, X, Y)
         return bev.permute(0, 3, 1, 2)        # (B, C, X, Y) view of channels-last storage
@@ -404,8 +283,16 @@ class LiftSplatShoot(nn.Module):
         return self.fast_inference and not self.training and not torch.is_grad_enabled()
 
     def forward(self, x, rots, trans, intrins, post_rots, post_trans):
+        if self._fast():
+            # inference on repo kernels only, NHWC bf16 from the images to the heads (monoforce_b200/encoder_fast.py)
+            if not x.is_cuda:
+                raise RuntimeError("monoforce_b200.LiftSplatShoot runs on CUDA only (sm_100a kernels, no CPU fallback)")
+            if int(self.nx[2]) != 1:
+                raise NotImplementedError("the fused lift-splat kernel assumes a single z voxel (zbound of lss_cfg.yaml)")
+            from . import encoder_fast
+            return encoder_fast.forward(self, x, self.cached_voxel_index(rots, trans, intrins, post_rots, post_trans))
         bev = self.get_voxels(x, rots, trans, intrins, post_rots, post_trans)
-        return self.bevencode.fast_forward(bev) if self._fast() else self.bevencode(bev)
+        return self.bevencode(bev)
 
     def from_pretrained(self, modelf):
         """Partial-state-dict loading like lss.py:293-302."""

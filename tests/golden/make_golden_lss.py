@@ -40,5 +40,22 @@ def main():
           os.path.getsize(path), "B")
 
 
+def default_size():
+    """lss_cfg.yaml sizes (4 cameras 256x416 -> 128x128 BEV), one scene: the reference's outputs only (inputs / weights are
+    reproducible from seeds)."""
+    from monoforce.models.terrain_encoder.lss import LiftSplatShoot
+    from helpers_lss import default_cfg
+    grid_conf, aug_conf = default_cfg()
+    torch.manual_seed(0)
+    net = perturb_for_test(LiftSplatShoot(grid_conf, aug_conf)).eval()
+    inputs = make_inputs(grid_conf, aug_conf, B=1, seed=3)
+    with torch.no_grad():
+        out = net(*inputs)
+    path = os.path.join(HERE, "lss_default_eval_B1.npz")
+    np.savez_compressed(path, **{k: v.numpy().astype(np.float32) for k, v in out.items()})
+    print({k: (tuple(v.shape), float(v.abs().mean())) for k, v in out.items()}, "->", os.path.getsize(path), "B")
+
+
 if __name__ == "__main__":
     main()
+    default_size()

@@ -1,0 +1,276 @@
+"""GPU tests of the encoder's inference kernels (K4 generalised tensor-core convolution, K7 memory-bound layers) against
+their fp32 torch statements (tests/helpers_fast_emul.py) on bf16-rounded inputs, through the C ABI.
+
+Tolerances: operands are bf16 (8 significant bits), accumulation fp32, outputs rounded to bf16: per element
+|err| <= 2^-8 |y| + accumulated operand rounding; checked as max |err| <= 2e-2 * max|y| and mean |err| <= 4e-3 * mean|y|.
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers_fast_emul as emul
+from helpers_mfb import load_golden, rel_err
+from helpers_lss import small_cfg, default_cfg, make_inputs, perturb_for_test
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def _close(got, want, max_tol=2e-2, mean_tol=4e-3):
+    got, want = got.float().cpu(), want.float().cpu()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    err = (got - want).abs()
+    assert err.max().item() <= max_tol * want.abs().max().item() + 1e-6, (err.max().item(), want.abs().max().item())
+    assert err.mean().item() <= mean_tol * want.abs().mean().item() + 1e-6, (err.mean().item(), want.abs().mean().item())
+
+
+CONV_CASES = [
+    # name,            N, H,  W,  Cin, Cout, K, stride, pad, act,            extras
+    ("3x3_s1_gelu",    2, 16, 26, 432, 512, 3, 1, 1, emul.ACT_GELU, {}),                 # camera Up.conv[0]: ragged tiles, Cin % 64 != 0
+    ("3x3_s2_relu",    2, 32, 32, 64, 128, 3, 2, 1, emul.ACT_RELU, {}),                   # ResNet layer2.0.conv1
+    ("1x1_s2_none",    2, 32, 32, 64, 128, 1, 2, 0, emul.ACT_NONE, {}),                   # ResNet downsample
+    ("7x7_s2_relu",    1, 64, 64, 64, 64, 7, 2, 3, emul.ACT_RELU, {}),                    # BevEncode.conv1
+    ("3x3_residual",   2, 24, 40, 128, 128, 3, 1, 1, emul.ACT_RELU, {"residual": True}),  # BasicBlock.conv2 + identity + ReLU
+    ("1x1_expand",     3, 20, 28, 16, 96, 1, 1, 0, emul.ACT_SILU, {}),                    # MBConv expand: Cin 16 (one quarter of a K chunk)
+    ("1x1_project",    3, 9, 13, 1152, 320, 1, 1, 0, emul.ACT_NONE, {"per_image": True}),            # MBConv project, SE folded per image
+    ("1x1_project_skip", 2, 16, 26, 672, 112, 1, 1, 0, emul.ACT_NONE, {"per_image": True, "residual": True}),
+    ("1x1_narrow_out", 2, 33, 17, 96, 24, 1, 1, 0, emul.ACT_NONE, {}),                    # Cout 24: one 64-column tile, 40 columns masked
+    ("3x3_s2_odd",     1, 17, 31, 40, 72, 3, 2, 1, emul.ACT_RELU, {}),                    # odd sizes, Cout % 64 != 0
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv2d_tcgen05_matches_fp32_statement(case):
+    from monoforce_b200 import ops
+    name, N, H, W, Cin, Cout, K, stride, pad, act, ex = case
+    g = torch.Generator().manual_seed(hash(name) % 1000)
+    x = _bf(torch.randn(N, H, W, Cin, generator=g))
+    wshape = (N, Cout, K, K, Cin) if ex.get("per_image") else (Cout, K, K, Cin)
+    w = _bf(torch.randn(*wshape, generator=g) * (1.0 / np.sqrt(K * K * Cin)))
+    scale = 0.5 + torch.rand(Cout, generator=g)
+    shift = 0.2 * torch.randn(Cout, generator=g)
+    Ho, Wo = emul.conv_out_size(H, K, stride, pad, pad), emul.conv_out_size(W, K, stride, pad, pad)
+    res = _bf(torch.randn(N, Ho, Wo, Cout, generator=g)) if ex.get("residual") else None
+    want = emul.conv2d_nhwc(x, w, scale, shift, act, stride=stride, pad=(pad, pad), out_hw=(Ho, Wo), residual=res)
+    got = ops.conv2d_nhwc(x.to(DEV), w.to(DEV), scale.to(DEV), shift.to(DEV), act, stride=stride, pad=(pad, pad), out_hw=(Ho, Wo),
+                          residual=None if res is None else res.to(DEV))
+    assert got.dtype == torch.bfloat16
+    _close(got, want)
+
+
+def test_conv2d_asymmetric_static_same_padding():
+    """TF 'SAME' at stride 2 pads one pixel more AFTER than before ((0,1) for k=3): only the low side is a parameter, the
+    high side is the TMA unit's zero fill."""
+    from monoforce_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = _bf(torch.randn(2, 16, 26, 64, generator=g))
+    w = _bf(torch.randn(64, 3, 3, 64, generator=g) / 24)
+    one, zero = torch.ones(64), torch.zeros(64)
+    want = emul.conv2d_nhwc(x, w, one, zero, emul.ACT_NONE, stride=2, pad=(0, 0), out_hw=(8, 13))
+    got = ops.conv2d_nhwc(x.to(DEV), w.to(DEV), one.to(DEV), zero.to(DEV), ops.ACT_NONE, stride=2, pad=(0, 0), out_hw=(8, 13))
+    _close(got, want)
+
+
+def test_conv2d_fused_heads_epilogue():
+    """Three 3x3 256 -> 128 convs + BN + GELU as one 256 -> 384 launch, each head's 1x1 conv + ScaledTanh / ReLU in the epilogue
+    (lss.py:117-139): fp32 (N,3,H,W) out, the 384-channel tensor never exists."""
+    from monoforce_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    N, H, W = 2, 24, 40
+    x = _bf(torch.randn(N, H, W, 256, generator=g))
+    w = _bf(torch.randn(384, 3, 3, 256, generator=g) / 48)
+    scale, shift = 0.5 + torch.rand(384, generator=g), 0.1 * torch.randn(384, generator=g)
+    head_w = torch.randn(384, generator=g) / 11
+    heads = (head_w, [0.05, 0.2, -0.1], [emul.HEAD_SCALED_TANH, emul.HEAD_RELU, emul.HEAD_RELU], [-1.0, 0.0, 0.0], [1.0, 0.0, 0.0])
+    want = emul.conv2d_nhwc(x, w, scale, shift, emul.ACT_GELU, pad=(1, 1), heads=heads)
+    got = ops.conv2d_nhwc(x.to(DEV), w.to(DEV), scale.to(DEV), shift.to(DEV), ops.ACT_GELU, pad=(1, 1),
+                          heads=(head_w.to(DEV),) + heads[1:])
+    assert got.dtype == torch.float32 and got.shape == (N, 3, H, W)
+    _close(got, want, max_tol=1e-2, mean_tol=3e-3)
+    assert (got[:, 1:] >= 0).all() and got[:, 0].abs().max() <= 1.0
+
+
+def test_conv2d_rejects_bad_arguments():
+    from monoforce_b200 import ops
+    x = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(64, 3, 3, 64, dtype=torch.bfloat16, device=DEV)
+    v = torch.zeros(64, device=DEV)
+    with pytest.raises(RuntimeError, match="stride"):
+        ops.conv2d_nhwc(x, w, v, v, 0, stride=3, pad=(1, 1), out_hw=(3, 3))
+    with pytest.raises(RuntimeError, match="does not fit"):
+        ops.conv2d_nhwc(x, w, v, v, 0, stride=1, pad=(1, 1), out_hw=(12, 8))
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        ops.conv2d_nhwc(x[..., :60].contiguous(), w[..., :60].contiguous(), v, v, 0, pad=(1, 1))
+
+
+@pytest.mark.parametrize("C,K,stride,pad,H,W", [(32, 3, 1, (1, 1), 40, 52), (96, 3, 2, (0, 1), 40, 52), (144, 5, 2, (1, 2), 20, 26),
+                                                (672, 5, 1, (2, 2), 16, 26), (1152, 3, 1, (1, 1), 8, 13), (240, 3, 2, (0, 1), 17, 9)])
+def test_depthwise_conv_bn_swish_and_pool(C, K, stride, pad, H, W):
+    from monoforce_b200 import ops
+    g = torch.Generator().manual_seed(C + K)
+    N = 3
+    x = _bf(torch.randn(N, H, W, C, generator=g))
+    w = torch.randn(K * K, C, generator=g) / K
+    shift = 0.3 * torch.randn(C, generator=g)
+    pool_want = torch.zeros(N, C)
+    want = emul.dwconv_bn_silu(x, w, shift, K, stride, pad, pool_want)
+    pool = torch.zeros(N, C, device=DEV)
+    got = ops.dwconv_bn_silu(x.to(DEV), w.to(DEV), shift.to(DEV), K, stride, pad, pool)
+    _close(got, want)
+    # the pool sums the bf16-rounded outputs: compare against that sum of the kernel's own output, then loosely vs fp32
+    assert rel_err(pool, got.float().sum((1, 2))) < 1e-4
+    assert rel_err(pool, pool_want) < 2e-2
+    again = ops.dwconv_bn_silu(x.to(DEV), w.to(DEV), shift.to(DEV), K, stride, pad, None)
+    assert torch.equal(again, got)
+
+
+def test_squeeze_excite_fold_into_projection_weights():
+    from monoforce_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for N, C, Sq, Cout in ((4, 32, 8, 16), (3, 1152, 48, 320), (2, 240, 10, 80)):
+        pool = torch.rand(N, C, generator=g) * 50
+        wr, br = torch.randn(Sq, C, generator=g) / C ** 0.5, 0.1 * torch.randn(Sq, generator=g)
+        we, be = torch.randn(C, Sq, generator=g) / Sq ** 0.5, 0.1 * torch.randn(C, generator=g)
+        proj = _bf(torch.randn(Cout, C, generator=g))
+        want = emul.se_fold(pool, 1 / 49.0, wr, br, we, be, proj)
+        got = ops.se_fold(pool.to(DEV), 1 / 49.0, wr.to(DEV), br.to(DEV), we.to(DEV), be.to(DEV), proj.to(DEV))
+        assert got.shape == (N, Cout, 1, 1, C) and got.dtype == torch.bfloat16
+        _close(got, want, max_tol=1e-2, mean_tol=3e-3)
+
+
+def test_stem_conv_and_upsample_concat_and_cast():
+    from monoforce_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    img = torch.randn(3, 3, 38, 50, generator=g)
+    w = torch.randn(3, 3, 3, 32, generator=g) / 5
+    shift = 0.2 * torch.randn(32, generator=g)
+    _close(ops.stem_conv(img.to(DEV), w.to(DEV), shift.to(DEV), (0, 1)), emul.stem_conv(img, w, shift, (0, 1)))
+    for scale, Cs, Cl, Cout in ((2, 112, 320, 432), (4, 64, 256, 320), (2, 0, 256, 256), (2, 16, 24, 64)):
+        low = _bf(torch.randn(2, 8, 13, Cl, generator=g))
+        skip = _bf(torch.randn(2, 8 * scale, 13 * scale, Cs, generator=g)) if Cs else None
+        want = emul.upsample_concat_nhwc(skip, low, (8 * scale, 13 * scale), Cout)
+        got = ops.upsample_concat_nhwc(None if skip is None else skip.to(DEV), low.to(DEV), (8 * scale, 13 * scale), Cout)
+        _close(got, want, max_tol=1e-2, mean_tol=3e-3)
+        if Cs:
+            assert torch.equal(got[..., :Cs].cpu(), skip)                 # the skip half is a pure copy
+    x = torch.randn(5, 7, 64, generator=g)
+    assert torch.equal(ops.cast_bf16(x.to(DEV)).cpu(), x.to(torch.bfloat16))
+
+
+def test_lift_splat_on_bf16_logits_matches_fp32_kernel():
+    from monoforce_b200 import ops
+    from monoforce_b200.terrain_encoder import LiftSplatShoot, _LiftSplat
+    gc, ac = small_cfg()
+    net = LiftSplatShoot(gc, ac)
+    B, N, D, C, fH, fW = 2, 4, net.D, net.camC, 8, 12
+    g = torch.Generator().manual_seed(4)
+    _, *calib = make_inputs(gc, ac, B, 9)
+    vox = net.voxel_index(net.get_geometry(*calib)).to(DEV)
+    logits = _bf(torch.randn(B * N, fH, fW, 128, generator=g)).to(DEV)
+    want = _LiftSplat.apply(logits[..., :D + C].float().contiguous(), vox.view(-1), B, N, D, C, 64, 64)
+    got = ops.lift_splat_bf16(logits, vox.view(-1), B, N, D, C, 64, 64)
+    assert rel_err(got, want) < 1e-5
+
+
+def _net(cfg_fn, seed=0):
+    from monoforce_b200.terrain_encoder import LiftSplatShoot
+    gc, ac = cfg_fn()
+    torch.manual_seed(seed)
+    return perturb_for_test(LiftSplatShoot(gc, ac)).eval().to(DEV), gc, ac
+
+
+def _fast(net, inputs):
+    net.fast_inference = True
+    with torch.no_grad():
+        out = net(*inputs)
+    net.fast_inference = False
+    return out
+
+
+def test_fast_path_stages_match_their_fp32_statement():
+    """Stage by stage on the GPU (bf16 kernels) vs the SAME host logic driven by the fp32 emulation: trunk endpoints,
+    camera Up, BEV backbone."""
+    import importlib
+    from monoforce_b200 import encoder_fast
+    net, gc, ac = _net(small_cfg)
+    x, *calib = make_inputs(gc, ac, 2, 6)
+    B, N = x.shape[:2]
+    imgs = x.view(B * N, *x.shape[2:])
+    with torch.no_grad():
+        P = encoder_fast.prepare(net)
+        f16, f32 = encoder_fast.trunk_endpoints(P, imgs.to(DEV))
+        up = encoder_fast.up_block(P["cam_up"], f16, f32, 2)
+        xb = _bf(torch.randn(2, 64, 64, 64))
+        g1, g3 = encoder_fast.bev_backbone(P, xb.to(DEV))
+        # the same functions with every kernel replaced by its fp32 statement, on the CPU copy of the prepared weights
+        cpu_net = net.__class__(gc, ac)
+        cpu_net.load_state_dict({k: v.cpu() for k, v in net.state_dict().items()})
+        cpu_net.eval()
+        old = encoder_fast.ops
+        encoder_fast.ops = emul
+        try:
+            Pc = encoder_fast.prepare(cpu_net)
+            e16, e32 = encoder_fast.trunk_endpoints(Pc, imgs)
+            eup = encoder_fast.up_block(Pc["cam_up"], e16, e32, 2)
+            h1, h3 = encoder_fast.bev_backbone(Pc, xb.float())
+        finally:
+            encoder_fast.ops = old
+    for name, got, want, tol in (("reduction_4", f16, e16, 0.05), ("reduction_5", f32, e32, 0.05), ("cam_up", up, eup, 0.05),
+                                 ("layer1", g1, h1, 0.03), ("layer3", g3, h3, 0.05)):
+        err = (got.float().cpu() - want).abs()
+        print(name, "max rel", (err.max() / want.abs().max()).item(), "mean rel", (err.mean() / want.abs().mean()).item())
+        assert err.max() <= tol * want.abs().max() and err.mean() <= 0.3 * tol * want.abs().mean(), name
+
+
+@pytest.mark.parametrize("which", ["small", "lss_cfg.yaml"])
+def test_fast_inference_whole_network_vs_reference_golden(which):
+    """The whole network on repo kernels (bf16 tensor-core path) vs the UNMODIFIED reference on the CPU (goldens minted by
+    tests/golden/make_golden_lss.py): the small fixture (2 scenes) and the reference's own lss_cfg.yaml sizes
+    (4 cameras 256x416 -> 128x128 BEV, 1 scene)."""
+    from monoforce_b200 import _lib
+    if which == "small":
+        net, gc, ac = _net(small_cfg)
+        inputs = [t.to(DEV) for t in make_inputs(gc, ac, 2, 1)]
+        g = load_golden("lss_small_eval_B2")
+    else:
+        net, gc, ac = _net(default_cfg)
+        inputs = [t.to(DEV) for t in make_inputs(gc, ac, 1, 3)]
+        g = load_golden("lss_default_eval_B1")
+    n0 = _lib.kernel_launches()
+    out = _fast(net, inputs)
+    launched = _lib.kernel_launches() - n0
+    assert launched >= 80, launched             # 1 stem + 16 x (<=4) MBConv + 4 + 1 + 1 + 1 + 15 + 3 + 2 kernels: the repo's, not cuDNN's
+    for k in ("geom", "terrain", "diff", "friction"):
+        got, want = out[k].float().cpu().numpy(), g[k]
+        assert got.shape == want.shape
+        err = np.abs(got - want)
+        print(which, k, "max abs", err.max(), "mean abs", err.mean(), "ref mean abs", np.abs(want).mean())
+        # bf16 operands through ~60 layers: a few percent of the output scale at worst, well under a percent on average
+        assert err.max() < 0.15 * max(np.abs(want).max(), 0.1) and err.mean() < 0.02 * np.abs(want).mean() + 2e-3, k
+    # with grad enabled (training / fine-tuning) the fp32 autograd path is used regardless of the flag
+    net.fast_inference = True
+    assert net(*inputs)["geom"].requires_grad
+
+
+def test_fast_path_follows_weight_updates_and_calibration_cache():
+    from monoforce_b200 import encoder_fast
+    net, gc, ac = _net(small_cfg)
+    inputs = [t.to(DEV) for t in make_inputs(gc, ac, 2, 2)]
+    a = _fast(net, inputs)
+    with torch.no_grad():
+        net.bevencode.up_friction[4].bias.add_(0.5)                     # e.g. an optimizer step / load_state_dict
+    b = _fast(net, inputs)
+    assert (b["friction"] - a["friction"]).mean().item() > 0.3 and torch.equal(a["geom"], b["geom"])
+    # the voxel index is cached per calibration: same tensors -> the same object; rebuilt tensors with equal values -> a hit too
+    v1 = net.cached_voxel_index(*inputs[1:])
+    assert net.cached_voxel_index(*inputs[1:]) is v1
+    assert net.cached_voxel_index(*[t.clone() for t in inputs[1:]]) is v1
+    moved = [t.clone() for t in inputs[1:]]
+    moved[1][..., 0] += 0.7
+    v2 = net.cached_voxel_index(*moved)
+    assert v2 is not v1 and not torch.equal(v1, v2)
+    assert torch.equal(v2, net.voxel_index(net.get_geometry(*moved)))

@@ -86,48 +86,6 @@ def test_network_restatement_matches_reference_golden_up_to_the_fused_stage():
     assert vox.dtype == torch.int32 and int((vox >= 0).sum()) > 0 and int(vox.max()) < 64 * 64
 
 
-def test_folded_inference_weights_match_module_path():
-    """Host logic of the eval fast path: BatchNorm folded into the convolutions (EfficientNet trunk, ResNet-18 BEV
-    backbone) + fused SiLU must reproduce the module path in fp32, and an in-place weight update must drop the fold."""
-    import torch
-    from helpers_lss import small_cfg
-    from monoforce_b200 import LiftSplatShoot
-    torch.manual_seed(0)
-    gc, ac = small_cfg()
-    net = LiftSplatShoot(gc, ac).eval()
-    for m in net.modules():
-        if isinstance(m, torch.nn.BatchNorm2d):
-            m.running_mean.normal_(0, 0.5); m.running_var.uniform_(0.5, 2.0)
-            m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.3)
-    rel = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
-    t = net.camencode.trunk
-    x = torch.randn(2, 3, 96, 128)
-    with torch.no_grad():
-        y = t._swish(t._bn0(t._conv_stem(x)))
-        feats, prev = [], y
-        for blk in t._blocks:
-            y = blk(y)
-            if prev.size(2) > y.size(2):
-                feats.append(prev)
-            prev = y
-        feats.append(y)
-        fast = t.fast_endpoints(x, dtype=torch.float32)
-        assert len(fast) == len(feats) == 5
-        for a, b in zip(fast, feats):
-            assert a.shape == b.shape and rel(a, b) < 1e-5
-        be = net.bevencode
-        xb = torch.randn(2, be.conv1.in_channels, 64, 64)
-        x1 = be.layer1(be.relu(be.bn1(be.conv1(xb)))); x3 = be.layer3(be.layer2(x1))
-        f1, f3 = be.fast_backbone_endpoints(xb, dtype=torch.float32)
-        assert rel(f1, x1) < 1e-5 and rel(f3, x3) < 1e-5
-        be.conv1.weight.mul_(1.1); t._conv_stem.weight.mul_(0.9)           # e.g. an optimizer step / load_state_dict
-        x1 = be.layer1(be.relu(be.bn1(be.conv1(xb))))
-        assert rel(be.fast_backbone_endpoints(xb, dtype=torch.float32)[0], x1) < 1e-5
-        y0 = t._swish(t._bn0(t._conv_stem(x)))
-        f0 = torch.nn.functional.silu(torch.nn.functional.conv2d(torch.nn.functional.pad(x, (0, 1, 0, 1)), *t.folded(torch.float32)["stem"], 2))
-        assert rel(f0, y0) < 1e-5
-
-
 def test_efficientnet_restatement_is_structurally_torchvision_b0():
     """The trunk internals cannot be pinned against efficientnet_pytorch 0.7.1 (absent from /root/reference and from this
     image), so they are anchored against an INDEPENDENT implementation of the same published architecture:
@@ -193,3 +151,53 @@ def test_efficientnet_restatement_is_structurally_torchvision_b0():
             y, z = mine(y), theirs(z)
             assert y.shape == z.shape and torch.allclose(y, z, rtol=1e-4, atol=1e-4), mine._block_args
         assert torch.allclose(ours._swish(ours._bn1(ours._conv_head(y))), tv.features[8](z), rtol=1e-4, atol=1e-4)
+
+
+def test_fast_path_host_logic_matches_module_path_in_fp32(monkeypatch):
+    """encoder_fast.prepare() + forward() with every kernel replaced by its fp32 torch statement (helpers_fast_emul) must
+    reproduce the module path: BatchNorm folding, squeeze-excite folded into per-image projection weights, static-same
+    padding, strides and output sizes of the ResNet layers, residual placement, concat order of the Up blocks and the
+    fused 1x1 heads.  (The kernels themselves are compared with the same emulation on the GPU, tests/test_encoder_gpu.py.)"""
+    import helpers_fast_emul as emul
+    from monoforce_b200 import LiftSplatShoot, encoder_fast
+    monkeypatch.setattr(encoder_fast, "ops", emul)
+    monkeypatch.setattr(encoder_fast, "WDTYPE", torch.float32)
+    gc, ac = small_cfg()
+    torch.manual_seed(0)
+    net = perturb_for_test(LiftSplatShoot(gc, ac)).eval()
+    x, *calib = make_inputs(gc, ac, 2, 1)
+    B, N = x.shape[:2]
+    rel = lambda a, b: ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+    with torch.no_grad():
+        P = encoder_fast.prepare(net)
+        assert encoder_fast.prepare(net) is P                                   # cached
+        # trunk endpoints
+        t = net.camencode.trunk
+        y = t._swish(t._bn0(t._conv_stem(x.view(B * N, *x.shape[2:]))))
+        feats, prev = [], y
+        for blk in t._blocks:
+            y = blk(y)
+            if prev.size(2) > y.size(2):
+                feats.append(prev)
+            prev = y
+        feats.append(y)
+        f16, f32 = encoder_fast.trunk_endpoints(P, x.view(B * N, *x.shape[2:]))
+        assert rel(f16.permute(0, 3, 1, 2), feats[3]) < 1e-4 and rel(f32.permute(0, 3, 1, 2), feats[4]) < 1e-4
+        # camera Up + depthnet
+        up = encoder_fast.up_block(P["cam_up"], f16, f32, 2)
+        assert rel(up.permute(0, 3, 1, 2), net.camencode.up1(feats[4], feats[3])) < 1e-4
+        # BEV backbone
+        be = net.bevencode
+        xb = torch.randn(2, be.conv1.in_channels, 64, 64)
+        x1 = be.layer1(be.relu(be.bn1(be.conv1(xb)))); x3 = be.layer3(be.layer2(x1))
+        g1, g3 = encoder_fast.bev_backbone(P, xb.permute(0, 2, 3, 1).contiguous())
+        assert rel(g1.permute(0, 3, 1, 2), x1) < 1e-4 and rel(g3.permute(0, 3, 1, 2), x3) < 1e-4
+        # whole network vs the reference golden (the lift-splat emulation stands in for K5)
+        vox = net.voxel_index(net.get_geometry(*calib))
+        out = encoder_fast.forward(net, x, vox)
+        g = load_golden("lss_small_eval_B2")
+        for k in ("geom", "terrain", "diff", "friction"):
+            assert out[k].shape == g[k].shape and np.allclose(out[k].numpy(), g[k], rtol=1e-3, atol=1e-4), k
+        # an in-place weight update must rebuild the folded weights
+        be.conv1.weight.mul_(1.1)
+        assert encoder_fast.prepare(net) is not P

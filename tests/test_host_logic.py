@@ -127,23 +127,6 @@ def test_unsupported_integration_mode_is_refused_not_run_as_euler():
         DPhysics(cfg, device="cpu")(cfg.z_grid.repeat(2, 1, 1), controls)
 
 
-def test_folded_weight_cache_follows_parameter_updates():
-    """the bf16 fold cache of Up / depthnet / heads must notice load_state_dict and in-place updates."""
-    from monoforce_b200.terrain_encoder import _folded
-    m = torch.nn.Conv2d(4, 4, 1)
-    calls = []
-    build = lambda: calls.append(1) or m.weight.detach().clone()
-    a = _folded(m, build)
-    assert _folded(m, build) is a and len(calls) == 1
-    with torch.no_grad():
-        m.weight.mul_(2.0)                                   # optimizer step / in-place edit
-    b = _folded(m, build)
-    assert len(calls) == 2 and torch.equal(b, m.weight)
-    m.load_state_dict({k: v * 0 + 1 for k, v in m.state_dict().items()})
-    c = _folded(m, build)
-    assert len(calls) == 3 and torch.equal(c, torch.ones_like(c))
-
-
 def test_efficientnet_trunk_weights_are_plumbed_and_absence_is_loud(tmp_path, monkeypatch):
     """lss.py:55 starts from ImageNet weights; here a weights file can be passed (argument or environment
     variable) and a missing one is announced instead of silently training from scratch."""

@@ -12,7 +12,6 @@ sys.path[:0] = [_R, os.path.join(_R, "tests")]
 import torch  # noqa: E402
 from helpers_lss import default_cfg, make_inputs  # noqa: E402
 from monoforce_b200 import LiftSplatShoot  # noqa: E402
-from monoforce_b200 import terrain_encoder as TE  # noqa: E402
 
 
 def main():
@@ -35,32 +34,33 @@ def main():
         e.record()
         marks.append((name, e))
 
+    from monoforce_b200 import encoder_fast as EF, ops
+
     def run():
         marks.clear()
         with torch.no_grad():
+            P = EF.prepare(net)
             mark("start")
             vox = net.cached_voxel_index(*cal)
             mark("voxel_index(cached)")
-            cam = net.camencode
-            feats = cam.trunk.fast_endpoints(x.view(B * N, C, H, W))
+            f16, f32 = EF.trunk_endpoints(P, x.view(B * N, C, H, W))
             mark("efficientnet trunk")
-            y = cam.up1.fast_nhwc(feats[4], feats[3])
+            y = EF.up_block(P["cam_up"], f16, f32, 2)
             mark("cam up1 (upsample+cat+2 conv)")
-            logits = cam.fast_logits_from_up(y) if hasattr(cam, "fast_logits_from_up") else None
-            if logits is None:
-                f = TE._folded(cam, lambda: TE._fold_padded_cout(cam.depthnet))
-                logits = TE.ops.conv_bn_act_nhwc(y, *f, TE.ops.ACT_NONE)[..., :cam.D + cam.C].float().contiguous()
-            mark("depthnet + slice/float")
+            logits = EF._conv(y, P["depthnet"], pad=0)
+            mark("depthnet")
             X, Y = int(net.nx[0]), int(net.nx[1])
-            bev = TE._LiftSplat.apply(logits, vox.view(-1), B, N, net.D, net.camC, X, Y).permute(0, 3, 1, 2)
-            mark("lift-splat")
-            be = net.bevencode
-            x1, x3 = be.fast_backbone_endpoints(bev)
-            mark("resnet stem + layer1-3")
-            yb = be.up1.fast_nhwc(x3, x1)
+            bev = ops.cast_bf16(ops.lift_splat_bf16(logits, vox.view(-1), B, N, net.D, net.camC, X, Y))
+            mark("lift-splat + cast")
+            x1, x3 = EF.bev_backbone(P, bev)
+            mark("conv1 7x7 + resnet layer1-3")
+            yb = EF.up_block(P["bev_up"], x1, x3, P["bev_up_scale"])
             mark("bev up1 (upsample+cat+2 conv)")
-            out = be.fast_heads(yb) if hasattr(be, "fast_heads") else None
-            mark("heads")
+            up = ops.upsample_concat_nhwc(None, yb, (yb.shape[1] * 2, yb.shape[2] * 2), yb.shape[3])
+            mark("heads upsample x2")
+            hs = P["heads"]
+            out = ops.conv2d_nhwc(up, hs["w"], hs["scale"], hs["shift"], hs["act"], pad=(1, 1), heads=P["head_epilogue"])
+            mark("heads conv + fused 1x1 epilogue")
         return out
 
     for _ in range(3):
