@@ -169,6 +169,7 @@ int mfb_lift_splat_forward_bf16(const void* logits, int row_stride, const void* 
  * mfb_se_fold_bf16: s = sigmoid(W_expand swish(W_reduce (pool * inv_hw) + b_reduce) + b_expand) per image and
  *   out_w[n,co,c] = proj_w[co,c] * s[c]: the excite scale folded into that image's projection matrix (consumed by
  *   mfb_conv2d_bf16 with per_image_weights).  w_reduce (Sq,C_se), w_expand (C_se,Sq) fp32; channels [C_se, C) are padding.
+ *   `pool` (N,C) is OVERWRITTEN with the excite scale s (two launches: the MLP once per image, then the scaling).
  * mfb_cast_f32_to_bf16: n scalars (multiple of 8). */
 int mfb_upsample_concat_nhwc_bf16(const void* skip, const void* low, void* out, int N, int H, int W, int C_skip, int Hl,
                                   int Wl, int C_low, int C_out, void* stream);
@@ -176,9 +177,19 @@ int mfb_stem_conv_bf16(const void* img, const void* w, const void* shift, void* 
                        int pad_h, int pad_w, void* stream);
 int mfb_dwconv_bn_silu_bf16(const void* x, const void* w, const void* shift, void* y, void* pool, int N, int H, int W, int C,
                             int Ho, int Wo, int K, int stride, int pad_h, int pad_w, void* stream);
-int mfb_se_fold_bf16(const void* pool, float inv_hw, const void* w_reduce, const void* b_reduce, const void* w_expand,
+int mfb_se_fold_bf16(void* pool, float inv_hw, const void* w_reduce, const void* b_reduce, const void* w_expand,
                      const void* b_expand, const void* proj_w, void* out_w, int N, int C, int C_se, int Sq, int Cout, void* stream);
 int mfb_cast_f32_to_bf16(const void* src, void* dst, long long n, void* stream);
+
+/* ---- between encoder, physics and planner, fp32 ---------------------------------------------------
+ * mfb_terrain_postproc: terrain = geom - diff (terrain_encoder/lss.py:158) and AvgPool2d(k) (scripts/train.py:96-99,234-235) of
+ *   the two maps the rollout reads, in one pass.  geom / diff / friction (B,1,X,Y) with `batch_stride` scalars between scenes;
+ *   terrain (B,1,X,Y), z_pooled / mu_pooled (B, X/k, Y/k); any output may be NULL.
+ * mfb_path_postproc: 4x4 poses (B,T,4,4) from Xs (B,T,3), Rs (B,T,3,3) (monoforce_ros/nodes/monoforce_node.py:80-85) and the
+ *   inclination cost mean_t|roll| + mean_t|pitch| (monoforce_ros/nodes/diff_physics.py:262-266, extrinsic xyz Euler angles). */
+int mfb_terrain_postproc(const void* geom, const void* diff, const void* friction, long long batch_stride, void* terrain,
+                         void* z_pooled, void* mu_pooled, int B, int X, int Y, int k, void* stream);
+int mfb_path_postproc(const void* Xs, const void* Rs, void* poses, void* cost, int B, int T, void* stream);
 
 /* ---- terrain encoder: dense convolution on tcgen05 tensor cores ----------------------------
  * Replaces the Conv2d -> BatchNorm2d(eval) [-> + residual] -> activation groups of the encoder's GEMM-shaped layers:

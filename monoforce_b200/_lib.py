@@ -20,7 +20,7 @@ EXPORTED_SYMBOLS = (
     "mfb_rollout_workspace_bytes", "mfb_rollout_forward", "mfb_rollout_backward", "mfb_rollout_forward_host",
     "mfb_lift_splat_forward", "mfb_lift_splat_backward", "mfb_lift_splat_forward_bf16", "mfb_conv_bn_act_bf16",
     "mfb_conv2d_bf16", "mfb_upsample_concat_nhwc_bf16", "mfb_stem_conv_bf16", "mfb_dwconv_bn_silu_bf16", "mfb_se_fold_bf16",
-    "mfb_cast_f32_to_bf16", "mfb_physics_loss",
+    "mfb_cast_f32_to_bf16", "mfb_terrain_postproc", "mfb_path_postproc", "mfb_physics_loss",
     "mfb_last_error", "mfb_abi_version", "mfb_kernel_launches", "mfb_release_scratch",
 )
 
@@ -102,6 +102,10 @@ def load() -> C.CDLL:
     lib.mfb_se_fold_bf16.restype = C.c_int
     lib.mfb_cast_f32_to_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
     lib.mfb_cast_f32_to_bf16.restype = C.c_int
+    lib.mfb_terrain_postproc.argtypes = [C.c_void_p] * 3 + [C.c_longlong] + [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p]
+    lib.mfb_terrain_postproc.restype = C.c_int
+    lib.mfb_path_postproc.argtypes = [C.c_void_p] * 4 + [C.c_int] * 2 + [C.c_void_p]
+    lib.mfb_path_postproc.restype = C.c_int
     lib.mfb_physics_loss.argtypes = ([C.c_void_p] * 4 + [C.c_int64] * 2 + [C.c_int] * 3 + [C.c_double, C.c_int] +
                                      [C.c_void_p] * 3 + [C.c_int, C.c_void_p])
     lib.mfb_physics_loss.restype = C.c_int

@@ -30,13 +30,28 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
+static int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
 template <int BLOCK_N>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p, cudaStream_t st) {
     auto kern = conv_bn_act_kernel<BLOCK_N>;
     const int smem = Smem<BLOCK_N>::kTotal;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return fail_status(MFB_ERR_CUDA, "conv: cudaFuncSetAttribute failed");
-    dim3 grid(p.tiles_w * p.tiles_h * p.N, (p.Cout + BLOCK_N - 1) / BLOCK_N);
+    const long long tiles = (long long)p.tiles_w * p.tiles_h * p.N * ((p.Cout + BLOCK_N - 1) / BLOCK_N);
+    const long long resident = 2ll * sm_count();             // persistent: 2 CTAs per SM walk the tiles
+    dim3 grid((unsigned)(tiles < resident ? tiles : resident));
     kern<<<grid, kThreads, smem, st>>>(mx, mw, p);
     count_launch();
     cudaError_t e = cudaGetLastError();

@@ -19,6 +19,7 @@
 // activation patch as a 4-D box {64 ch, TW*s, TH*s, 1} with traversal strides {1,s,s,1} (out-of-image rows/columns are
 // zero-filled by the TMA unit == the conv's zero padding) and the matching weight slab {64, BLOCK_N}; both land in
 // 128-byte-swizzled K-major shared tiles, the canonical UMMA operand layout, so no im2col buffer ever exists.
+// Persistent CTAs (2 per SM) walk the tiles; two TMEM accumulators overlap one tile's epilogue with the next tile's MMAs.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2-5 = epilogue (tcgen05.ld -> scale/shift (+residual) -> activation -> bf16 16-byte stores | head dot product).
 #pragma once
@@ -64,7 +65,7 @@ struct Smem {
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarrierOffset = kStages * kStageBytes;
-    static constexpr int kTotal = kBarrierOffset + 256 + 1024;    // barriers + slack for 1024-byte alignment
+    static constexpr int kTotal = kBarrierOffset + 256 + 1024;    // barriers (2 x kStages + 4) + TMEM slot + slack for 1024-byte alignment
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -154,6 +155,15 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(s_addr(bar)) : "memory");
+}
+
+// Persistent: grid = min(tiles, 2 CTAs per SM); every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... with
+// (output-channel block) fastest, so the CTAs that share an activation patch run at the same time and hit it in L2.
+// Three pipelines (guide: "canonical Blackwell GEMM"): smem full/empty (TMA <-> MMA, kStages deep, runs across tile
+// boundaries so the next tile's operands stream in during this tile's epilogue), TMEM full/empty (MMA <-> epilogue, two
+// accumulators of BLOCK_N columns: the MMAs of tile i+1 overlap the epilogue of tile i), and the tile walk itself.
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
@@ -162,17 +172,14 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     using S = Smem<BLOCK_N>;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarrierOffset);
     uint64_t* empty = full + kStages;
-    uint64_t* acc_ready = empty + kStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_ready + 1);
+    uint64_t* acc_full = empty + kStages;       // [2]
+    uint64_t* acc_empty = acc_full + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile coordinates
-    const int tile = blockIdx.x;
-    const int tw = tile % p.tiles_w;
-    const int th = (tile / p.tiles_w) % p.tiles_h;
-    const int n = tile / (p.tiles_w * p.tiles_h);
-    const int w0 = tw * kTileW, h0 = th * kTileH;
-    const int n0 = blockIdx.y * BLOCK_N;
+    const int n_blocks = (p.Cout + BLOCK_N - 1) / BLOCK_N;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+    const long long total = (long long)tiles_per_img * p.N * n_blocks;
     // Cin need not be a multiple of 64: the last chunk's channels beyond Cin are outside the tensor map's extent, which the
     // TMA unit fills with zeros (for the weights too, whose rows are KH*KW*Cin long), so they add nothing to the sum
     const int chunks_per_tap = (p.Cin + kBlockK - 1) / kBlockK;
@@ -182,127 +189,152 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_w) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(acc_ready, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }     // 4 epilogue warps drain an accumulator
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N);          // BLOCK_N fp32 accumulator columns (power of two >= 32)
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BLOCK_N);      // two fp32 accumulators of BLOCK_N columns (power of two >= 32)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_acc = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            for (int i = 0; i < k_iters; ++i) {
-                const int s = i % kStages;
-                const uint32_t round = i / kStages;
-                mbar_wait(empty + s, (round & 1) ^ 1);
-                const int tap = i / chunks_per_tap, c0 = (i - tap * chunks_per_tap) * kBlockK;
-                const int dy = tap / p.KW, dx = tap - dy * p.KW;
-                uint8_t* a_dst = smem + s * S::kStageBytes;
-                uint8_t* b_dst = a_dst + S::kABytes;
-                mbar_expect_tx(full + s, S::kStageBytes);
-                // input pixel of output (h, w) under tap (dy, dx): (stride*h + dy - pad_h, stride*w + dx - pad_w); the
-                // tensor map traverses W and H with step `stride`, so the box lands as TH x TW consecutive rows
-                tma_load_4d(a_dst, &tmap_x, full + s, c0, w0 * p.stride + dx - p.pad_w, h0 * p.stride + dy - p.pad_h, n);
-                if (p.per_image_w) tma_load_3d(b_dst, &tmap_w, full + s, tap * p.Cin + c0, n0, n);
-                else tma_load_2d(b_dst, &tmap_w, full + s, tap * p.Cin + c0, n0);
+            uint32_t it = 0;
+            for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+                const int nb = (int)(t % n_blocks);
+                const long long pt = t / n_blocks;
+                const int tw = (int)(pt % p.tiles_w), th = (int)((pt / p.tiles_w) % p.tiles_h), n = (int)(pt / tiles_per_img);
+                const int w0 = tw * kTileW, h0 = th * kTileH, n0 = nb * BLOCK_N;
+                for (int i = 0; i < k_iters; ++i, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
+                    const int tap = i / chunks_per_tap, c0 = (i - tap * chunks_per_tap) * kBlockK;
+                    const int dy = tap / p.KW, dx = tap - dy * p.KW;
+                    uint8_t* a_dst = smem + s * S::kStageBytes;
+                    uint8_t* b_dst = a_dst + S::kABytes;
+                    mbar_expect_tx(full + s, S::kStageBytes);
+                    // input pixel of output (h, w) under tap (dy, dx): (stride*h + dy - pad_h, stride*w + dx - pad_w); the
+                    // tensor map traverses W and H with step `stride`, so the box lands as TH x TW consecutive rows
+                    tma_load_4d(a_dst, &tmap_x, full + s, c0, w0 * p.stride + dx - p.pad_w, h0 * p.stride + dy - p.pad_h, n);
+                    if (p.per_image_w) tma_load_3d(b_dst, &tmap_w, full + s, tap * p.Cin + c0, n0, n);
+                    else tma_load_2d(b_dst, &tmap_w, full + s, tap * p.Cin + c0, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer (one thread) =====
             constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
-            for (int i = 0; i < k_iters; ++i) {
-                const int s = i % kStages;
-                const uint32_t round = i / kStages;
-                mbar_wait(full + s, round & 1);
+            uint32_t it = 0, lt = 0;
+            for (long long t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+                const uint32_t as = lt & 1;
+                mbar_wait(acc_empty + as, ((lt >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint8_t* a_src = smem + s * S::kStageBytes;
-                const uint64_t a_desc = make_kmajor_sw128_desc(a_src);
-                const uint64_t b_desc = make_kmajor_sw128_desc(a_src + S::kABytes);
+                const uint32_t tmem_acc = tmem_base + as * BLOCK_N;
+                for (int i = 0; i < k_iters; ++i, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(full + s, (it / kStages) & 1);
+                    tc_fence_after();
+                    const uint8_t* a_src = smem + s * S::kStageBytes;
+                    const uint64_t a_desc = make_kmajor_sw128_desc(a_src);
+                    const uint64_t b_desc = make_kmajor_sw128_desc(a_src + S::kABytes);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
-                    umma_bf16(tmem_acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0);
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) address field
+                        umma_bf16(tmem_acc, a_desc + 2 * k, b_desc + 2 * k, idesc, (i | k) != 0);
+                    }
+                    umma_commit(empty + s);                      // frees the stage once these MMAs have read it
                 }
-                umma_commit(empty + s);                      // frees the stage once these MMAs have read it
+                umma_commit(acc_full + as);                      // accumulator complete
             }
-            umma_commit(acc_ready);                          // accumulator complete
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
         const int q = warp & 3;
-        mbar_wait(acc_ready, 0);
-        tc_fence_after();
         const int m = q * 32 + lane;                         // accumulator row == pixel inside the patch
         const int hh = m / kTileW, ww = m - hh * kTileW;
-        const int h = h0 + hh, w = w0 + ww;
-        const bool in_image = (h < p.Ho) && (w < p.Wo);
-        const long long pix = ((long long)n * p.Ho + h) * p.Wo + w;
-        if (p.head_out != nullptr) {
-            // fused 1x1 head: one output channel per BLOCK_N-channel group (this CTA's group = blockIdx.y)
-            float dot = 0.f;
+        uint32_t lt = 0;
+        for (long long t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+            const int nb = (int)(t % n_blocks);
+            const long long pt = t / n_blocks;
+            const int tw = (int)(pt % p.tiles_w), th = (int)((pt / p.tiles_w) % p.tiles_h), n = (int)(pt / tiles_per_img);
+            const int n0 = nb * BLOCK_N;
+            const int h = th * kTileH + hh, w = tw * kTileW + ww;
+            const bool in_image = (h < p.Ho) && (w < p.Wo);
+            const long long pix = ((long long)n * p.Ho + h) * p.Wo + w;
+            const uint32_t as = lt & 1;
+            mbar_wait(acc_full + as, (lt >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
+            if (p.head_out != nullptr) {
+                // fused 1x1 head: one output channel per BLOCK_N-channel group (this tile's group = nb)
+                float dot = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_acc + c, r);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int co = n0 + c + j;
-                    const float v = apply_act(__uint_as_float(r[j]) * __ldg(p.scale + co) + __ldg(p.shift + co), p.act);
-                    dot = fmaf(v, __ldg(p.head_w + co), dot);
+                    for (int j = 0; j < 32; ++j) {
+                        const int co = n0 + c + j;
+                        const float v = apply_act(__uint_as_float(r[j]) * __ldg(p.scale + co) + __ldg(p.shift + co), p.act);
+                        dot = fmaf(v, __ldg(p.head_w + co), dot);
+                    }
                 }
-            }
-            if (in_image) {
-                const int g = blockIdx.y;
-                float o = dot + p.head_b[g];
-                if (p.head_act[g] == kHeadRelu) o = fmaxf(o, 0.f);
-                else if (p.head_act[g] == kHeadScaledTanh) o = p.head_lo[g] + (p.head_hi[g] - p.head_lo[g]) * (tanhf(o) + 1.f) * 0.5f;
-                p.head_out[((long long)n * gridDim.y + g) * p.Ho * p.Wo + (long long)h * p.Wo + w] = o;
-            }
-        } else {
-            __nv_bfloat16* out = p.y + pix * p.Cout + n0;
-            const __nv_bfloat16* rsd = p.res ? p.res + pix * p.Cout + n0 : nullptr;
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + c, r);
                 if (in_image) {
+                    float o = dot + p.head_b[nb];
+                    if (p.head_act[nb] == kHeadRelu) o = fmaxf(o, 0.f);
+                    else if (p.head_act[nb] == kHeadScaledTanh) o = p.head_lo[nb] + (p.head_hi[nb] - p.head_lo[nb]) * (tanhf(o) + 1.f) * 0.5f;
+                    p.head_out[((long long)n * n_blocks + nb) * p.Ho * p.Wo + (long long)h * p.Wo + w] = o;
+                }
+            } else {
+                __nv_bfloat16* out = p.y + pix * p.Cout + n0;
+                const __nv_bfloat16* rsd = p.res ? p.res + pix * p.Cout + n0 : nullptr;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    if (n0 + c >= p.Cout) break;              // warp-uniform: nothing but padding columns left
+                    uint32_t r[32];
+                    tmem_ld32(tmem_acc + c, r);
+                    if (in_image) {
 #pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8) {
-                        const int co = n0 + c + 8 * g8;
-                        if (co < p.Cout) {                    // Cout is a multiple of 8, not necessarily of BLOCK_N
-                            const float4 sc0 = __ldg(reinterpret_cast<const float4*>(p.scale + co)), sc1 = __ldg(reinterpret_cast<const float4*>(p.scale + co + 4));
-                            const float4 sh0 = __ldg(reinterpret_cast<const float4*>(p.shift + co)), sh1 = __ldg(reinterpret_cast<const float4*>(p.shift + co + 4));
-                            const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-                            const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-                            float v[8];
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const int co = n0 + c + 8 * g8;
+                            if (co < p.Cout) {                    // Cout is a multiple of 8, not necessarily of BLOCK_N
+                                const float4 sc0 = __ldg(reinterpret_cast<const float4*>(p.scale + co)), sc1 = __ldg(reinterpret_cast<const float4*>(p.scale + co + 4));
+                                const float4 sh0 = __ldg(reinterpret_cast<const float4*>(p.shift + co)), sh1 = __ldg(reinterpret_cast<const float4*>(p.shift + co + 4));
+                                const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                                const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+                                float v[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[8 * g8 + j]), sc[j], sh[j]);
-                            if (rsd) {
-                                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rsd + c + 8 * g8));
-                                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                                for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[8 * g8 + j]), sc[j], sh[j]);
+                                if (rsd) {
+                                    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rsd + c + 8 * g8));
+                                    const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(r2[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+                                    for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(r2[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+                                }
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(apply_act(v[2 * j], p.act), apply_act(v[2 * j + 1], p.act));
+                                    pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
+                                }
+                                *reinterpret_cast<uint4*>(out + c + 8 * g8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                             }
-                            uint32_t pk[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const __nv_bfloat162 b2 = __floats2bfloat162_rn(apply_act(v[2 * j], p.act), apply_act(v[2 * j + 1], p.act));
-                                pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
-                            }
-                            *reinterpret_cast<uint4*>(out + c + 8 * g8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         }
                     }
                 }
             }
+            // this warp has read everything it needs from the accumulator: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + as);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_acc, BLOCK_N);
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BLOCK_N);
 }
 
 }  // namespace conv

@@ -130,103 +130,124 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// depthwise k x k conv + shift + swish; pool[n,c] += sum over this CTA's pixels of the output (fp32)
-// x (N,H,W,C), y (N,Ho,Wo,C) bf16; w (K*K, C) fp32 (BN scale folded); grid = (pixel-group tiles, N)
+// depthwise k x k conv + shift + swish; pool[n,c] += sum over the pixels of the (bf16-rounded) output
+// x (N,H,W,C), y (N,Ho,Wo,C) bf16; w (K*K, C) fp32 (BN scale folded).
+// Work item = a strip of kDwStrip consecutive output pixels of one row x one 8-channel group: the input row segment of a
+// tap row is loaded once and slides over the strip (k + (S-1)*stride loads per tap row instead of k*S), weights once per
+// tap.  A CTA owns all C/8 channel groups of P = blockDim / G strips at a time and walks kDwRows strips per thread, so its
+// squeeze-excite partial sums leave as ONE atomicAdd per channel for up to P * kDwRows * kDwStrip pixels.
 // ---------------------------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(256)
+constexpr int kDwStrip = 4, kDwRows = 8;
+
+template <int K, int STRIDE>
+__global__ void __launch_bounds__(256, 2)
 dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
-              __nv_bfloat16* __restrict__ y, float* __restrict__ pool, int H, int W, int C, int Ho, int Wo, int stride,
-              int ph, int pw) {
+              __nv_bfloat16* __restrict__ y, float* __restrict__ pool, int H, int W, int C, int Ho, int Wo, int ph, int pw) {
     extern __shared__ float pool_s[];                      // C partial sums of this CTA
+    constexpr int S = kDwStrip;
+    constexpr int IN = K + (S - 1) * STRIDE;               // input pixels a strip needs per tap row
     const int n = blockIdx.y;
     const int G = C >> 3;
-    for (int i = threadIdx.x; i < C; i += blockDim.x) pool_s[i] = 0.f;
-    __syncthreads();
-    const long long per_img = (long long)Ho * Wo * G;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int g = (int)(i % G);
+    const int P = blockDim.x / G;                          // strips in flight per CTA (host guarantees >= 1)
+    const int g = threadIdx.x % G, slot = threadIdx.x / G;
     const int c = g << 3;
-    float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        // what this thread adds to the pool
-    if (i < per_img) {
-        const int pix = (int)(i / G);
-        const int wo = pix % Wo, ho = pix / Wo;
-        float acc[8];
-        {
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + c)), s1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
-            acc[0] = s0.x; acc[1] = s0.y; acc[2] = s0.z; acc[3] = s0.w; acc[4] = s1.x; acc[5] = s1.y; acc[6] = s1.z; acc[7] = s1.w;
-        }
-        const __nv_bfloat16* base = x + (long long)n * H * W * C + c;
-#pragma unroll
-        for (int dy = 0; dy < K; ++dy) {
-            const int hi = ho * stride + dy - ph;
-            if (hi < 0 || hi >= H) continue;
-#pragma unroll
-            for (int dx = 0; dx < K; ++dx) {
-                const int wi = wo * stride + dx - pw;
-                if (wi < 0 || wi >= W) continue;
-                float v[8];
-                unpack8(ld8(base + ((long long)hi * W + wi) * C), v);
-                const float* wr = w + (dy * K + dx) * C + c;
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr)), w1 = __ldg(reinterpret_cast<const float4*>(wr + 4));
-                acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
-                acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
-                acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
-                acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = silu(acc[k]);
-        const Bf8 o = pack8(acc);
-        *reinterpret_cast<Bf8*>(y + ((long long)n * Ho * Wo + pix) * C + c) = o;
-        unpack8(o, r);                                         // the pool sees what the next layer sees: bf16-rounded values
-    }
+    const int strips_w = (Wo + S - 1) / S;
+    const int n_strips = Ho * strips_w;
     if (pool) {
-        // lanes l and l + j*G of a warp hold the same channel group: fold them onto lane l < G first, so the shared-memory
-        // atomics below hit distinct addresses within a warp (the first MBConv blocks have only 4..18 channel groups)
-        const int lane = threadIdx.x & 31;
-        if (G < 32) {
-            float t[8];
+        for (int i = threadIdx.x; i < C; i += blockDim.x) pool_s[i] = 0.f;
+        __syncthreads();
+    }
+    float sh[8];
+    {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + c)), s1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
+        sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
+    }
+    float psum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const __nv_bfloat16* xin = x + (long long)n * H * W * C + c;
+    __nv_bfloat16* yout = y + (long long)n * Ho * Wo * C + c;
+    if (slot < P) {
+        for (int r = 0; r < kDwRows; ++r) {
+            const int sid = (blockIdx.x * kDwRows + r) * P + slot;
+            if (sid >= n_strips) break;
+            const int ho = sid / strips_w, wo0 = (sid - ho * strips_w) * S;
+            float acc[S][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) t[k] = r[k];
-            for (int src = lane + G; src - lane < 32; src += G) {
+            for (int j = 0; j < S; ++j)
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float o = __shfl_sync(0xffffffffu, t[k], src & 31);
-                    if (src < 32) r[k] += o;
+                for (int k = 0; k < 8; ++k) acc[j][k] = sh[k];
+            const int wi0 = wo0 * STRIDE - pw;
+#pragma unroll
+            for (int dy = 0; dy < K; ++dy) {
+                const int hi = ho * STRIDE + dy - ph;
+                if (hi < 0 || hi >= H) continue;
+                const __nv_bfloat16* row = xin + (long long)hi * W * C;
+                Bf8 v[IN];                                     // kept packed (4 registers per pixel), unpacked at use
+#pragma unroll
+                for (int i = 0; i < IN; ++i) {
+                    const int wi = wi0 + i;
+                    if (wi >= 0 && wi < W) v[i] = ld8(row + (long long)wi * C);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) v[i].v[k] = __floats2bfloat162_rn(0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int dx = 0; dx < K; ++dx) {
+                    const float* wr = w + (dy * K + dx) * C + c;
+                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr)), w1 = __ldg(reinterpret_cast<const float4*>(wr + 4));
+                    const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int j = 0; j < S; ++j) {
+                        float t[8];
+                        unpack8(v[j * STRIDE + dx], t);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(t[k], wk[k], acc[j][k]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                if (wo0 + j < Wo) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[j][k] = silu(acc[j][k]);
+                    const Bf8 o = pack8(acc[j]);
+                    *reinterpret_cast<Bf8*>(yout + ((long long)ho * Wo + wo0 + j) * C) = o;
+                    float rr[8];
+                    unpack8(o, rr);                                // the pool sees what the next layer sees: bf16-rounded values
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) psum[k] += rr[k];
                 }
             }
         }
-        if (lane < G) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) atomicAdd(pool_s + c + k, r[k]);
-        }
     }
     if (pool) {
+        if (slot < P) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(pool_s + c + k, psum[k]);      // P-way contention at most (P = 256 / G)
+        }
         __syncthreads();
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const float v = pool_s[c];
-            if (v != 0.f) atomicAdd(pool + (long long)n * C + c, v);
+        for (int i = threadIdx.x; i < C; i += blockDim.x) {
+            const float v = pool_s[i];
+            if (v != 0.f) atomicAdd(pool + (long long)n * C + i, v);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// squeeze-excite folded into per-image projection weights.  grid = (ceil(Cout / kRows), N), 256 threads.
-//   m = pool[n,:] * inv_hw;  r = swish(Wr m + br)  (Sq);  s = sigmoid(We r + be)  (C);  out[n,co,c] = proj[co,c] * s[c]
+// squeeze-excite folded into per-image projection weights, two launches:
+//   se_mlp   grid N:  m = pool[n,:] * inv_hw;  r = swish(Wr m + br) (Sq);  s = sigmoid(We r + be) (C);  pool[n,:] <- s
+//   se_scale grid (ceil(Cout / kSeRows), N):  out[n,co,c] = proj[co,c] * s[n,c]
 // Wr (Sq, Cse), We (Cse, Sq): Cse = the block's real channel count; channels [Cse, C) are padding: s = 0 there.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSeRows = 16;
 constexpr int kSeMaxC = 1280, kSeMaxSq = 64;
 __global__ void __launch_bounds__(256)
-se_fold_kernel(const float* __restrict__ pool, float inv_hw, const float* __restrict__ Wr, const float* __restrict__ br,
-               const float* __restrict__ We, const float* __restrict__ be, const __nv_bfloat16* __restrict__ proj,
-               __nv_bfloat16* __restrict__ out, int C, int Cse, int Sq, int Cout) {
+se_mlp_kernel(float* __restrict__ pool, float inv_hw, const float* __restrict__ Wr, const float* __restrict__ br,
+              const float* __restrict__ We, const float* __restrict__ be, int C, int Cse, int Sq) {
     __shared__ float m[kSeMaxC];
     __shared__ float r[kSeMaxSq];
-    __shared__ float s[kSeMaxC];
-    const int n = blockIdx.y;
-    for (int c = threadIdx.x; c < Cse; c += blockDim.x) m[c] = pool[(long long)n * C + c] * inv_hw;
+    float* row = pool + (long long)blockIdx.x * C;
+    for (int c = threadIdx.x; c < Cse; c += blockDim.x) m[c] = row[c] * inv_hw;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int q = warp; q < Sq; q += 8) {
@@ -244,18 +265,23 @@ se_fold_kernel(const float* __restrict__ pool, float inv_hw, const float* __rest
             for (int q = 0; q < Sq; ++q) a = fmaf(__ldg(We + (long long)c * Sq + q), r[q], a);
             v = __fdividef(1.f, 1.f + __expf(-a));
         }
-        s[c] = v;
+        row[c] = v;
     }
-    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+se_scale_kernel(const float* __restrict__ s, const __nv_bfloat16* __restrict__ proj, __nv_bfloat16* __restrict__ out, int C, int Cout) {
+    const int n = blockIdx.y;
     const int row0 = blockIdx.x * kSeRows;
     const int G = C >> 3;
+    const float* sn = s + (long long)n * C;
     for (int i = threadIdx.x; i < kSeRows * G; i += blockDim.x) {
         const int row = row0 + i / G, c = (i % G) << 3;
         if (row >= Cout) break;
         float v[8];
         unpack8(ld8(proj + (long long)row * C + c), v);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] *= s[c + k];
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(sn + c)), s1 = __ldg(reinterpret_cast<const float4*>(sn + c + 4));
+        v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
         *reinterpret_cast<Bf8*>(out + ((long long)n * Cout + row) * C + c) = pack8(v);
     }
 }
@@ -267,6 +293,84 @@ cast_kernel(const float4* __restrict__ src, Bf8* __restrict__ dst, long long n8)
         const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         dst[i] = pack8(f);
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Between the encoder and the physics: terrain = geom - diff (lss.py:158) and the AvgPool2d(k) that brings the
+// encoder's grid to the physics resolution (train.py:96-99,234-235), for the two maps the rollout reads, in one pass.
+// geom / diff / friction: (B,1,X,Y) fp32 with batch stride `bs` (they may be channel slices of one (B,3,X,Y) tensor).
+// One thread per pooled cell: writes its k x k terrain cells and the two pooled means.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+terrain_postproc_kernel(const float* __restrict__ geom, const float* __restrict__ diff, const float* __restrict__ fric,
+                        long long bs, float* __restrict__ terrain, float* __restrict__ z_pool, float* __restrict__ mu_pool,
+                        int B, int X, int Y, int k) {
+    const int Xp = X / k, Yp = Y / k;
+    const long long total = (long long)B * Xp * Yp;
+    const float inv = 1.f / (float)(k * k);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int yp = (int)(i % Yp);
+        const int xp = (int)((i / Yp) % Xp);
+        const int b = (int)(i / ((long long)Yp * Xp));
+        float sz = 0.f, sm = 0.f;
+        for (int dx = 0; dx < k; ++dx) {
+            const long long row = (long long)(xp * k + dx) * Y + yp * k;
+            for (int dy = 0; dy < k; ++dy) {
+                const float t = __ldg(geom + b * bs + row + dy) - __ldg(diff + b * bs + row + dy);
+                if (terrain) terrain[(long long)b * X * Y + row + dy] = t;
+                sz += t;
+                sm += __ldg(fric + b * bs + row + dy);
+            }
+        }
+        if (z_pool) z_pool[i] = sz * inv;
+        if (mu_pool) mu_pool[i] = sm * inv;
+    }
+    // rows / columns beyond the last full window are dropped by AvgPool2d but still belong to `terrain`
+    if (terrain && (X % k || Y % k)) {
+        const long long cells = (long long)B * X * Y;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (long long)gridDim.x * blockDim.x) {
+            const int y = (int)(i % Y), x = (int)((i / Y) % X);
+            if (x >= Xp * k || y >= Yp * k) {
+                const int b = (int)(i / ((long long)X * Y));
+                const long long o = (long long)x * Y + y;
+                terrain[i] = __ldg(geom + b * bs + o) - __ldg(diff + b * bs + o);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Planner post-processing of a rollout: 4x4 poses (monoforce_node.py:80-85, diff_physics.py:246-250) and the
+// inclination cost mean_t |roll| + mean_t |pitch| with (roll, pitch) the extrinsic x-y-z Euler angles of R
+// (diff_physics.py:262-266: scipy Rotation.from_matrix(R).as_euler('xyz')): roll = atan2(R21, R22), pitch = -asin(R20).
+// One warp per trajectory.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+path_postproc_kernel(const float* __restrict__ Xs, const float* __restrict__ Rs, float* __restrict__ poses,
+                     float* __restrict__ cost, int B, int T) {
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float acc = 0.f;
+    for (int t = lane; t < T; t += 32) {
+        const float* R = Rs + ((long long)b * T + t) * 9;
+        const float* x = Xs + ((long long)b * T + t) * 3;
+        float r[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) r[i] = __ldg(R + i);
+        if (poses) {
+            float4* P = reinterpret_cast<float4*>(poses + ((long long)b * T + t) * 16);
+            P[0] = make_float4(r[0], r[1], r[2], __ldg(x));
+            P[1] = make_float4(r[3], r[4], r[5], __ldg(x + 1));
+            P[2] = make_float4(r[6], r[7], r[8], __ldg(x + 2));
+            P[3] = make_float4(0.f, 0.f, 0.f, 1.f);
+        }
+        acc += fabsf(atan2f(r[7], r[8])) + fabsf(asinf(fminf(fmaxf(-r[6], -1.f), 1.f)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (cost && lane == 0) cost[b] = acc / (float)T;
 }
 
 static int after_launch(const char* what) {
@@ -321,27 +425,57 @@ int mfb_dwconv_bn_silu_bf16(const void* x, const void* w, const void* shift, voi
     if (K != 3 && K != 5) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: kernel size must be 3 or 5");
     if (stride != 1 && stride != 2) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: stride must be 1 or 2");
     if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)w | (uintptr_t)shift) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "dwconv: tensors must be 16-byte aligned");
-    const long long per_img = (long long)Ho * Wo * (C >> 3);
-    dim3 grid((unsigned)((per_img + 255) / 256), (unsigned)N);
+    const int G = C >> 3;
+    if (G > 256) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: at most 2048 channels");
+    const int P = 256 / G;
+    const int threads = ((P * G + 31) / 32) * 32;
+    const long long n_strips = (long long)Ho * ((Wo + kDwStrip - 1) / kDwStrip);
+    dim3 grid((unsigned)((n_strips + (long long)P * kDwRows - 1) / ((long long)P * kDwRows)), (unsigned)N);
     const size_t smem = (size_t)C * sizeof(float);
-    auto args = [&](auto kern) {
-        kern<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const float*)w, (const float*)shift,
-                                                        (__nv_bfloat16*)y, (float*)pool, H, W, C, Ho, Wo, stride, pad_h, pad_w);
+    auto go = [&](auto kern) {
+        kern<<<grid, threads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const float*)w, (const float*)shift,
+                                                            (__nv_bfloat16*)y, (float*)pool, H, W, C, Ho, Wo, pad_h, pad_w);
     };
-    if (K == 3) args(dwconv_kernel<3>); else args(dwconv_kernel<5>);
+    if (K == 3 && stride == 1) go(dwconv_kernel<3, 1>);
+    else if (K == 3) go(dwconv_kernel<3, 2>);
+    else if (stride == 1) go(dwconv_kernel<5, 1>);
+    else go(dwconv_kernel<5, 2>);
     return after_launch("dwconv");
 }
 
-int mfb_se_fold_bf16(const void* pool, float inv_hw, const void* w_reduce, const void* b_reduce, const void* w_expand,
+int mfb_se_fold_bf16(void* pool, float inv_hw, const void* w_reduce, const void* b_reduce, const void* w_expand,
                      const void* b_expand, const void* proj_w, void* out_w, int N, int C, int C_se, int Sq, int Cout, void* stream) {
     if (!pool || !w_reduce || !b_reduce || !w_expand || !b_expand || !proj_w || !out_w) return fail_status(MFB_ERR_INVALID_ARGUMENT, "se_fold: NULL pointer");
     if (N < 1 || Cout < 1 || Sq < 1 || Sq > kSeMaxSq || C < 8 || C > kSeMaxC || (C & 7) || C_se < 1 || C_se > C)
         return fail_status(MFB_ERR_UNSUPPORTED, "se_fold: need C % 8 == 0, C <= 1280, Sq <= 64, C_se <= C");
+    if ((uintptr_t)pool & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "se_fold: pool must be 16-byte aligned");
+    se_mlp_kernel<<<(unsigned)N, 256, 0, (cudaStream_t)stream>>>((float*)pool, inv_hw, (const float*)w_reduce, (const float*)b_reduce,
+                                                                 (const float*)w_expand, (const float*)b_expand, C, C_se, Sq);
+    if (int rc = after_launch("se_mlp")) return rc;
     dim3 grid((unsigned)((Cout + kSeRows - 1) / kSeRows), (unsigned)N);
-    se_fold_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)pool, inv_hw, (const float*)w_reduce, (const float*)b_reduce,
-                                                           (const float*)w_expand, (const float*)b_expand, (const __nv_bfloat16*)proj_w,
-                                                           (__nv_bfloat16*)out_w, C, C_se, Sq, Cout);
-    return after_launch("se_fold");
+    se_scale_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)pool, (const __nv_bfloat16*)proj_w, (__nv_bfloat16*)out_w, C, Cout);
+    return after_launch("se_scale");
+}
+
+int mfb_terrain_postproc(const void* geom, const void* diff, const void* friction, long long batch_stride, void* terrain,
+                         void* z_pooled, void* mu_pooled, int B, int X, int Y, int k, void* stream) {
+    if (!geom || !diff || !friction) return fail_status(MFB_ERR_INVALID_ARGUMENT, "terrain_postproc: NULL pointer");
+    if (B < 1 || X < 1 || Y < 1 || k < 1 || k > X || k > Y || batch_stride < (long long)X * Y)
+        return fail_status(MFB_ERR_INVALID_ARGUMENT, "terrain_postproc: bad sizes");
+    const long long total = (long long)B * (X / k) * (Y / k);
+    terrain_postproc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)geom, (const float*)diff, (const float*)friction, batch_stride, (float*)terrain, (float*)z_pooled,
+        (float*)mu_pooled, B, X, Y, k);
+    return after_launch("terrain_postproc");
+}
+
+int mfb_path_postproc(const void* Xs, const void* Rs, void* poses, void* cost, int B, int T, void* stream) {
+    if (!Xs || !Rs || (!poses && !cost)) return fail_status(MFB_ERR_INVALID_ARGUMENT, "path_postproc: NULL pointer");
+    if (B < 1 || T < 1) return fail_status(MFB_ERR_INVALID_ARGUMENT, "path_postproc: sizes must be positive");
+    if ((uintptr_t)poses & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "path_postproc: poses must be 16-byte aligned");
+    path_postproc_kernel<<<(unsigned)((B + 3) / 4), 128, 0, (cudaStream_t)stream>>>((const float*)Xs, (const float*)Rs, (float*)poses,
+                                                                                    (float*)cost, B, T);
+    return after_launch("path_postproc");
 }
 
 int mfb_cast_f32_to_bf16(const void* src, void* dst, long long n, void* stream) {

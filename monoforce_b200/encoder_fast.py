@@ -223,6 +223,7 @@ def forward(net, imgs, vox):
     if P["heads_fused"]:
         out = ops.conv2d_nhwc(up, hs["w"], hs["scale"], hs["shift"], hs["act"], pad=(1, 1), heads=P["head_epilogue"])
         geom, diff, friction = out[:, 0:1], out[:, 1:2], out[:, 2:3]
+        return {'geom': geom, 'terrain': ops.terrain_postproc(geom, diff, friction, 1)[0], 'diff': diff, 'friction': friction}
     else:      # outC != 1: the 1x1 output convolutions go through torch on the (B,X,Y,384) tensor
         z = _conv(up, hs).permute(0, 3, 1, 2).float()
         heads = (net.bevencode.up_geom, net.bevencode.up_diff, net.bevencode.up_friction)

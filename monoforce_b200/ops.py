@@ -183,3 +183,37 @@ def lift_splat_bf16(logits, vox, B, N, D, Cc, X, Y):
         _lib.check(lib.mfb_lift_splat_forward_bf16(_p(logits), rs, _p(vox), _p(bev), B, N, D, Cc, fH, fW, X, Y, _stream(logits.device)),
                    "mfb_lift_splat_forward_bf16")
     return bev
+
+
+def terrain_postproc(geom, diff, friction, pool=1, want_terrain=True):
+    """terrain = geom - diff (lss.py:158) and AvgPool2d(pool) of (terrain, friction) (train.py:96-99,234-235) in one kernel.
+    geom / diff / friction: (B,1,X,Y) fp32 CUDA (channel slices of one tensor are fine).  Returns (terrain | None,
+    terrain_pooled (B,1,X/pool,Y/pool), friction_pooled)."""
+    _need_cuda(geom, "terrain_postproc")
+    B, one, X, Y = geom.shape
+    assert one == 1 and diff.shape == geom.shape == friction.shape and geom.dtype == torch.float32
+    bs = {t.stride(0) for t in (geom, diff, friction)}
+    ok = len(bs) == 1 and all(t.stride()[2:] == (Y, 1) for t in (geom, diff, friction))
+    if not ok:
+        geom, diff, friction = geom.contiguous(), diff.contiguous(), friction.contiguous()
+    terrain = torch.empty(B, 1, X, Y, dtype=torch.float32, device=geom.device) if want_terrain else None
+    zp = torch.empty(B, 1, X // pool, Y // pool, dtype=torch.float32, device=geom.device)
+    mp = torch.empty_like(zp)
+    lib = _lib.load()
+    with torch.cuda.device(geom.device):
+        _lib.check(lib.mfb_terrain_postproc(_p(geom), _p(diff), _p(friction), geom.stride(0), _p(terrain), _p(zp), _p(mp), B, X, Y, pool,
+                                            _stream(geom.device)), "mfb_terrain_postproc")
+    return terrain, zp, mp
+
+
+def path_postproc(Xs, Rs, want_poses=True):
+    """(poses (B,T,4,4) | None, inclination cost (B,)) of a rollout: monoforce_node.py:80-85, diff_physics.py:262-266."""
+    _need_cuda(Xs, "path_postproc")
+    B, T, _ = Xs.shape
+    Xs, Rs = Xs.detach().float().contiguous(), Rs.detach().float().contiguous()
+    poses = torch.empty(B, T, 4, 4, dtype=torch.float32, device=Xs.device) if want_poses else None
+    cost = torch.empty(B, dtype=torch.float32, device=Xs.device)
+    lib = _lib.load()
+    with torch.cuda.device(Xs.device):
+        _lib.check(lib.mfb_path_postproc(_p(Xs), _p(Rs), _p(poses), _p(cost), B, T, _stream(Xs.device)), "mfb_path_postproc")
+    return poses, cost

@@ -104,3 +104,8 @@ def lift_splat_bf16(logits, vox, B, N, D, Cc, X, Y):
             ok = idx >= 0
             bev[b].index_add_(0, idx[ok], contrib.reshape(-1, Cc)[ok])
     return bev.view(B, X, Y, Cc)
+
+
+def terrain_postproc(geom, diff, friction, pool=1, want_terrain=True):
+    t = geom - diff
+    return (t if want_terrain else None), F.avg_pool2d(t, pool), F.avg_pool2d(friction, pool)

@@ -274,3 +274,29 @@ def test_fast_path_follows_weight_updates_and_calibration_cache():
     v2 = net.cached_voxel_index(*moved)
     assert v2 is not v1 and not torch.equal(v1, v2)
     assert torch.equal(v2, net.voxel_index(net.get_geometry(*moved)))
+
+
+def test_terrain_and_path_postprocessing_kernels():
+    """F4: terrain = geom - diff + AvgPool2d(k) of the physics inputs in one pass (lss.py:158, train.py:96-99,234-235); poses and
+    the inclination cost of the planner (monoforce_node.py:80-85, diff_physics.py:262-266 via scipy's Euler angles)."""
+    from scipy.spatial.transform import Rotation
+    from monoforce_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    heads = torch.randn(3, 3, 50, 36, generator=g).to(DEV)
+    geom, diff, fric = heads[:, 0:1], heads[:, 1:2], heads[:, 2:3]
+    for k in (1, 2, 4, 7):
+        terrain, zp, mp = ops.terrain_postproc(geom, diff, fric, k)
+        assert torch.equal(terrain, geom - diff)
+        assert torch.allclose(zp, torch.nn.functional.avg_pool2d(geom - diff, k), atol=1e-6)
+        assert torch.allclose(mp, torch.nn.functional.avg_pool2d(fric, k), atol=1e-6)
+    B, T = 5, 77
+    rot = Rotation.random(B * T, random_state=3)
+    Rs = torch.as_tensor(rot.as_matrix(), dtype=torch.float32).view(B, T, 3, 3)
+    Xs = torch.randn(B, T, 3, generator=g)
+    poses, cost = ops.path_postproc(Xs.to(DEV), Rs.to(DEV))
+    rpy = torch.as_tensor(Rotation.from_matrix(Rs.view(-1, 3, 3).numpy()).as_euler('xyz'))
+    want = rpy[:, 0].reshape(B, -1).abs().mean(-1) + rpy[:, 1].reshape(B, -1).abs().mean(-1)
+    assert torch.allclose(cost.cpu().double(), want, rtol=1e-4, atol=1e-5)
+    ref = torch.zeros(B, T, 4, 4)
+    ref[:, :, :3, 3], ref[:, :, :3, :3], ref[:, :, 3, 3] = Xs, Rs, 1.0
+    assert torch.equal(poses.cpu(), ref)
