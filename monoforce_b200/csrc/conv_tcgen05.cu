@@ -43,9 +43,9 @@ static int sm_count() {
     return cached[dev];
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int ACT, bool HEAD>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p, cudaStream_t st) {
-    auto kern = conv_bn_act_kernel<BLOCK_N>;
+    auto kern = conv_bn_act_kernel<BLOCK_N, ACT, HEAD>;
     const int smem = Smem<BLOCK_N>::kTotal;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return fail_status(MFB_ERR_CUDA, "conv: cudaFuncSetAttribute failed");
@@ -133,7 +133,20 @@ extern "C" int mfb_conv2d_bf16(const mfb_conv_desc* d, const void* x, const void
         p.head_b[i] = d->head_bias[i]; p.head_lo[i] = d->head_lo[i]; p.head_hi[i] = d->head_hi[i]; p.head_act[i] = d->head_act[i];
     }
     cudaStream_t st = (cudaStream_t)stream;
-    return block_n == 128 ? launch<128>(mx, mw, p, st) : launch<64>(mx, mw, p, st);
+    if (head) {
+        if (d->act != kGelu) return fail_status(MFB_ERR_UNSUPPORTED, "conv: head mode is instantiated for the GELU heads of BevEncode only");
+        return block_n == 128 ? launch<128, kGelu, true>(mx, mw, p, st) : launch<64, kGelu, true>(mx, mw, p, st);
+    }
+    switch (d->act * 2 + (block_n == 128)) {
+        case kNone * 2: return launch<64, kNone, false>(mx, mw, p, st);
+        case kNone * 2 + 1: return launch<128, kNone, false>(mx, mw, p, st);
+        case kRelu * 2: return launch<64, kRelu, false>(mx, mw, p, st);
+        case kRelu * 2 + 1: return launch<128, kRelu, false>(mx, mw, p, st);
+        case kGelu * 2: return launch<64, kGelu, false>(mx, mw, p, st);
+        case kGelu * 2 + 1: return launch<128, kGelu, false>(mx, mw, p, st);
+        case kSilu * 2: return launch<64, kSilu, false>(mx, mw, p, st);
+        default: return launch<128, kSilu, false>(mx, mw, p, st);
+    }
 }
 
 // ABI v2 entry point: KS x KS, stride 1, "same" padding (kept for existing callers; forwards to mfb_conv2d_bf16)

@@ -20,8 +20,11 @@
 // zero-filled by the TMA unit == the conv's zero padding) and the matching weight slab {64, BLOCK_N}; both land in
 // 128-byte-swizzled K-major shared tiles, the canonical UMMA operand layout, so no im2col buffer ever exists.
 // Persistent CTAs (2 per SM) walk the tiles; two TMEM accumulators overlap one tile's epilogue with the next tile's MMAs.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2-5 = epilogue (tcgen05.ld -> scale/shift (+residual) -> activation -> bf16 16-byte stores | head dot product).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2-9 = epilogue (tcgen05.ld -> scale/shift (+residual) -> activation -> bf16 16-byte stores | head dot product);
+// warp w reads TMEM lane quadrant w % 4 and the column half (w - 2) / 4.  The activation is a template parameter: the
+// epilogue of the memory-bound layers is instruction-latency-bound (ncu: 12 cycles per issued instruction with 2 warps per
+// scheduler), so per-element branches and libm calls are what it cannot afford.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -36,7 +39,8 @@ constexpr int kTileW = 16;        // patch width  (pixels)
 constexpr int kTileH = 8;         // patch height (pixels)
 constexpr int kBlockK = 64;       // bf16 channels per K chunk = one 128-byte swizzle row
 constexpr int kStages = 3;       // 3 x 32 KB: two CTAs fit one SM, so one CTA's epilogue overlaps the other's MMAs
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;      // two per TMEM lane quadrant: each takes half of the tile's columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 enum Act : int { kNone = 0, kRelu = 1, kGelu = 2, kSilu = 3 };
 enum HeadAct : int { kHeadNone = 0, kHeadRelu = 1, kHeadScaledTanh = 2 };
@@ -65,7 +69,7 @@ struct Smem {
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarrierOffset = kStages * kStageBytes;
-    static constexpr int kTotal = kBarrierOffset + 256 + 1024;    // barriers (2 x kStages + 4) + TMEM slot + slack for 1024-byte alignment
+    static constexpr int kTotal = kBarrierOffset + 256 + 512 + 1024;    // barriers (2 x kStages + 4) + TMEM slot + 128 head partials + slack for 1024-byte alignment
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -148,10 +152,29 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-    if (act == kRelu) return fmaxf(v, 0.f);
-    if (act == kGelu) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));     // nn.GELU() (erf form)
-    if (act == kSilu) return __fdividef(v, 1.f + __expf(-v));                        // x * sigmoid(x)
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 output rounding): 2 SFU ops + 10 FMA-class
+// instructions, no branches (libm's erff is ~3x that with a data-dependent branch)
+__device__ __forceinline__ float erf_fast(float x) {
+    const float ax = fabsf(x);
+    const float t = rcp_approx(fmaf(0.3275911f, ax, 1.f));
+    float poly = fmaf(t, 1.061405429f, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    const float e = ex2_approx(ax * ax * -1.4426950408889634f);
+    return copysignf(fmaf(-poly, e, 1.f), x);
+}
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v) {
+    if (ACT == kRelu) return fmaxf(v, 0.f);
+    if (ACT == kGelu) return 0.5f * v * (1.f + erf_fast(v * 0.70710678118654752f));      // nn.GELU() (erf form)
+    if (ACT == kSilu) { const float h = 0.5f * v; return fmaf(h, tanh_approx(h), h); }   // x sigmoid(x) = x/2 (1 + tanh(x/2))
     return v;
 }
 
@@ -164,7 +187,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Three pipelines (guide: "canonical Blackwell GEMM"): smem full/empty (TMA <-> MMA, kStages deep, runs across tile
 // boundaries so the next tile's operands stream in during this tile's epilogue), TMEM full/empty (MMA <-> epilogue, two
 // accumulators of BLOCK_N columns: the MMAs of tile i+1 overlap the epilogue of tile i), and the tile walk itself.
-template <int BLOCK_N>
+template <int BLOCK_N, int ACT, bool HEAD>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -189,7 +212,7 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmap_w) : "memory");
         for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 4); }     // 4 epilogue warps drain an accumulator
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, kEpiWarps); }     // every epilogue warp drains its part
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, 2 * BLOCK_N);      // two fp32 accumulators of BLOCK_N columns (power of two >= 32)
@@ -251,10 +274,13 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
-        const int q = warp & 3;
+        // ===== epilogue: warp w owns TMEM lane quadrant w % 4 and column half (w - 2) / 4 =====
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        constexpr int kColsPerWarp = BLOCK_N / 2;
+        const int c_lo = half * kColsPerWarp;
         const int m = q * 32 + lane;                         // accumulator row == pixel inside the patch
         const int hh = m / kTileW, ww = m - hh * kTileW;
+        float* head_part = reinterpret_cast<float*>(tmem_slot + 4);     // [kBlockM] partial head dots of the upper column half
         uint32_t lt = 0;
         for (long long t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
             const int nb = (int)(t % n_blocks);
@@ -268,31 +294,35 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             mbar_wait(acc_full + as, (lt >> 1) & 1);
             tc_fence_after();
             const uint32_t tmem_acc = tmem_base + as * BLOCK_N + ((uint32_t)(q * 32) << 16);
-            if (p.head_out != nullptr) {
+            if (HEAD) {
                 // fused 1x1 head: one output channel per BLOCK_N-channel group (this tile's group = nb)
                 float dot = 0.f;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 32) {
+                for (int c = c_lo; c < c_lo + kColsPerWarp; c += 32) {
                     uint32_t r[32];
                     tmem_ld32(tmem_acc + c, r);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int co = n0 + c + j;
-                        const float v = apply_act(__uint_as_float(r[j]) * __ldg(p.scale + co) + __ldg(p.shift + co), p.act);
+                        const float v = apply_act<ACT>(fmaf(__uint_as_float(r[j]), __ldg(p.scale + co), __ldg(p.shift + co)));
                         dot = fmaf(v, __ldg(p.head_w + co), dot);
                     }
                 }
-                if (in_image) {
-                    float o = dot + p.head_b[nb];
+                // the two warps of a lane quadrant each hold half of the dot product: combine through shared memory
+                if (half == 1) head_part[m] = dot;
+                asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");
+                if (half == 0 && in_image) {
+                    float o = dot + head_part[m] + p.head_b[nb];
                     if (p.head_act[nb] == kHeadRelu) o = fmaxf(o, 0.f);
                     else if (p.head_act[nb] == kHeadScaledTanh) o = p.head_lo[nb] + (p.head_hi[nb] - p.head_lo[nb]) * (tanhf(o) + 1.f) * 0.5f;
                     p.head_out[((long long)n * n_blocks + nb) * p.Ho * p.Wo + (long long)h * p.Wo + w] = o;
                 }
+                asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");      // head_part is free for the next tile
             } else {
                 __nv_bfloat16* out = p.y + pix * p.Cout + n0;
                 const __nv_bfloat16* rsd = p.res ? p.res + pix * p.Cout + n0 : nullptr;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 32) {
+                for (int c = c_lo; c < c_lo + kColsPerWarp; c += 32) {
                     if (n0 + c >= p.Cout) break;              // warp-uniform: nothing but padding columns left
                     uint32_t r[32];
                     tmem_ld32(tmem_acc + c, r);
@@ -317,7 +347,7 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                                 uint32_t pk[4];
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(apply_act(v[2 * j], p.act), apply_act(v[2 * j + 1], p.act));
+                                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(apply_act<ACT>(v[2 * j]), apply_act<ACT>(v[2 * j + 1]));
                                     pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
                                 }
                                 *reinterpret_cast<uint4*>(out + c + 8 * g8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

@@ -264,7 +264,8 @@ def test_fast_path_follows_weight_updates_and_calibration_cache():
     with torch.no_grad():
         net.bevencode.up_friction[4].bias.add_(0.5)                     # e.g. an optimizer step / load_state_dict
     b = _fast(net, inputs)
-    assert (b["friction"] - a["friction"]).mean().item() > 0.3 and torch.equal(a["geom"], b["geom"])
+    # (fp32 atomics in the lift-splat and in the squeeze-excite pool make two runs agree to rounding, not bit for bit)
+    assert (b["friction"] - a["friction"]).mean().item() > 0.3 and torch.allclose(a["geom"], b["geom"], atol=2e-3)
     # the voxel index is cached per calibration: same tensors -> the same object; rebuilt tensors with equal values -> a hit too
     v1 = net.cached_voxel_index(*inputs[1:])
     assert net.cached_voxel_index(*inputs[1:]) is v1
