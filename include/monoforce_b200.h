@@ -162,7 +162,8 @@ int mfb_lift_splat_forward_bf16(const void* logits, int row_stride, const void* 
  *   `torch.cat([x2, self.up(x1)], dim=1)` of Up.forward (lss.py:44-46; nn.Upsample(bilinear, align_corners=True)) and, with
  *   C_skip = 0, the x2 up-sampling in front of the BEV heads (lss.py:118,126,133).
  * mfb_stem_conv_bf16: EfficientNet-B0 stem (efficientnet_pytorch 0.7.1 `_conv_stem` + `_bn0` + swish, lss.py:78):
- *   img (N,3,H,W) fp32 NCHW -> y (N,Ho,Wo,32); w (3,3,3,32) fp32 [dy][dx][ci][co] with the BatchNorm scale folded in.
+ *   img (N,3,H,W) fp32 NCHW -> y (N,Ho,Wo,32); w (3,3,3,32) fp32 [dy][dx][ci][co] with the BatchNorm scale folded in and
+ *   shift (32,) are HOST pointers (3.5 KB, passed to the kernel by value so that they feed the FMAs from the constant bank).
  * mfb_dwconv_bn_silu_bf16: MBConv depthwise K x K (3 | 5) convolution, stride 1 | 2, low-side padding (pad_h, pad_w), folded
  *   BatchNorm, swish; `pool` (N,C) fp32, if not NULL, accumulates the sum of the outputs over the pixels (the squeeze of the
  *   squeeze-excite block; zero it first).  w (K*K, C) fp32, shift (C,) fp32.

@@ -43,10 +43,10 @@ static int sm_count() {
     return cached[dev];
 }
 
-template <int BLOCK_N, int ACT, bool HEAD>
-static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p, cudaStream_t st) {
-    auto kern = conv_bn_act_kernel<BLOCK_N, ACT, HEAD>;
-    const int smem = Smem<BLOCK_N>::kTotal;
+template <int BLOCK_N, int ACT, bool HEAD, int STAGES, bool XPOSE>
+static int launch_v(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p, cudaStream_t st) {
+    auto kern = conv_bn_act_kernel<BLOCK_N, ACT, HEAD, STAGES, XPOSE>;
+    const int smem = Smem<BLOCK_N, STAGES, XPOSE>::kTotal;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return fail_status(MFB_ERR_CUDA, "conv: cudaFuncSetAttribute failed");
     const long long tiles = (long long)p.tiles_w * p.tiles_h * p.N * ((p.Cout + BLOCK_N - 1) / BLOCK_N);
@@ -57,6 +57,14 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail_status(MFB_ERR_CUDA, std::string("conv launch: ") + cudaGetErrorString(e));
     return MFB_OK;
+}
+
+// memory-bound layers (few K chunks): 2 stages + transposed (coalesced) stores; deep-K layers: 3 stages, direct stores
+template <int BLOCK_N, int ACT, bool HEAD>
+static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p, cudaStream_t st) {
+    const int k_iters = p.KH * p.KW * ((p.Cin + kBlockK - 1) / kBlockK);
+    if (!HEAD && k_iters <= 18) return launch_v<BLOCK_N, ACT, false, 2, true>(mx, mw, p, st);
+    return launch_v<BLOCK_N, ACT, HEAD, 3, false>(mx, mw, p, st);
 }
 
 }  // namespace conv
@@ -81,6 +89,7 @@ extern "C" int mfb_conv2d_bf16(const mfb_conv_desc* d, const void* x, const void
     if (d->Cin < 8 || d->Cin % 8) return fail_status(MFB_ERR_UNSUPPORTED, "conv: Cin must be a multiple of 8 (16-byte rows for TMA)");
     if (d->Cout < 8 || d->Cout % 8) return fail_status(MFB_ERR_UNSUPPORTED, "conv: Cout must be a multiple of 8");
     if (d->act < kNone || d->act > kSilu) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: unknown activation");
+    if (d->Cout > kMaxParamChannels - 128) return fail_status(MFB_ERR_UNSUPPORTED, "conv: at most 1152 output channels");
     if (((uintptr_t)x | (uintptr_t)wgt | (uintptr_t)y | (uintptr_t)residual) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: tensors must be 16-byte aligned");
     const int block_n = d->Cout > 64 ? 128 : 64;
     if (((uintptr_t)scale | (uintptr_t)shift) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: scale / shift must be 16-byte aligned");

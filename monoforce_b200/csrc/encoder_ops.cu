@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstring>
 #include <string>
 
 #include "../../include/monoforce_b200.h"
@@ -27,9 +28,12 @@ namespace enc {
 
 struct alignas(16) Bf8 { __nv_bfloat162 v[4]; };
 
+// bf16 -> fp32 is a 16-bit shift: one SHL and one LOP per pair (the library conversion goes through more instructions)
 __device__ __forceinline__ void unpack8(const Bf8& b, float* f) {
+    const uint4 u = *reinterpret_cast<const uint4*>(&b);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(b.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+    for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
 }
 __device__ __forceinline__ Bf8 pack8(const float* f) {
     Bf8 b;
@@ -38,7 +42,13 @@ __device__ __forceinline__ Bf8 pack8(const float* f) {
     return b;
 }
 __device__ __forceinline__ Bf8 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const Bf8*>(p); }
-__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+// x sigmoid(x) = x/2 (1 + tanh(x/2)): one SFU op + 2 FMA-class instructions (tanh.approx: 2^-11 relative, below bf16 rounding)
+__device__ __forceinline__ float silu(float v) {
+    const float h = 0.5f * v;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // out[n,h,w, 0:Cs] = skip[n,h,w,:];  out[n,h,w, Cs:Cs+Cl] = bilinear(low)[n,h,w,:] (align_corners=True);  rest = 0
@@ -85,17 +95,16 @@ upsample_concat_kernel(const __nv_bfloat16* __restrict__ skip, const __nv_bfloat
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// stem: img (N,3,H,W) fp32 NCHW -> y (N,Ho,Wo,32) bf16 NHWC; 3x3 stride 2, low-side padding (ph, pw); w (3,3,3,32) fp32
-// [dy][dx][ci][co] with BN scale folded; y = swish(conv + shift)
+// stem: img (N,3,H,W) fp32 NCHW -> y (N,Ho,Wo,32) bf16 NHWC; 3x3 stride 2, low-side padding (ph, pw); weights (3,3,3,32)
+// fp32 [dy][dx][ci][co] with the BN scale folded; y = swish(conv + shift).  The 864 weights + 32 shifts travel BY VALUE as
+// a kernel parameter: they sit in the constant bank and feed the FMAs as immediate operands (no load instruction per
+// FMA; from shared memory the kernel was LDS-bound: 216 LDS.128 per 864 FMAs, 0.45 ms at 64 x 512 x 512).
 // ---------------------------------------------------------------------------------------------------------------
+struct StemWeights { float w[27 * 32]; float shift[32]; };
+
 __global__ void __launch_bounds__(128)
-stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ shift,
-                 __nv_bfloat16* __restrict__ y, int N, int H, int W, int Ho, int Wo, int ph, int pw) {
-    __shared__ float ws[27 * 32];
-    __shared__ float sh[32];
-    for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) ws[i] = w[i];
-    if (threadIdx.x < 32) sh[threadIdx.x] = shift[threadIdx.x];
-    __syncthreads();
+stem_conv_kernel(const float* __restrict__ img, const __grid_constant__ StemWeights sw, __nv_bfloat16* __restrict__ y, int N,
+                 int H, int W, int Ho, int Wo, int ph, int pw) {
     const long long total = (long long)N * Ho * Wo;
     for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
         const int wo = (int)(pix % Wo);
@@ -103,7 +112,7 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, con
         const int n = (int)(pix / ((long long)Wo * Ho));
         float acc[32];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = sh[c];
+        for (int c = 0; c < 32; ++c) acc[c] = sw.shift[c];
         const float* base = img + (long long)n * 3 * H * W;
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
@@ -115,9 +124,8 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, con
 #pragma unroll
                 for (int ci = 0; ci < 3; ++ci) {
                     const float v = ok ? __ldg(base + ((long long)ci * H + hi) * W + wi) : 0.f;
-                    const float* wr = ws + ((dy * 3 + dx) * 3 + ci) * 32;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+                    for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, sw.w[((dy * 3 + dx) * 3 + ci) * 32 + c], acc[c]);
                 }
             }
         }
@@ -130,19 +138,21 @@ stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// depthwise k x k conv + shift + swish; pool[n,c] += sum over the pixels of the (bf16-rounded) output
+// depthwise k x k conv + shift + swish; pool[n,c] += sum over the pixels of the output (fp32)
 // x (N,H,W,C), y (N,Ho,Wo,C) bf16; w (K*K, C) fp32 (BN scale folded).
 // Work item = a strip of kDwStrip consecutive output pixels of one row x one 8-channel group: the input row segment of a
 // tap row is loaded once and slides over the strip (k + (S-1)*stride loads per tap row instead of k*S), weights once per
-// tap.  A CTA owns all C/8 channel groups of P = blockDim / G strips at a time and walks kDwRows strips per thread, so its
-// squeeze-excite partial sums leave as ONE atomicAdd per channel for up to P * kDwRows * kDwStrip pixels.
+// tap.  A CTA owns all C/8 channel groups of P = blockDim / G strips at a time and walks `rows` strips per thread (up to 8;
+// fewer on the small feature maps, so that the grid still fills the GPU a few times over), so its squeeze-excite partial
+// sums leave as ONE atomicAdd per channel for up to P * rows * kDwStrip pixels.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kDwStrip = 4, kDwRows = 8;
+constexpr int kDwStrip = 4, kDwMaxRows = 8;
 
 template <int K, int STRIDE>
 __global__ void __launch_bounds__(256, 2)
 dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
-              __nv_bfloat16* __restrict__ y, float* __restrict__ pool, int H, int W, int C, int Ho, int Wo, int ph, int pw) {
+              __nv_bfloat16* __restrict__ y, float* __restrict__ pool, int H, int W, int C, int Ho, int Wo, int ph, int pw,
+              int rows) {
     extern __shared__ float pool_s[];                      // C partial sums of this CTA
     constexpr int S = kDwStrip;
     constexpr int IN = K + (S - 1) * STRIDE;               // input pixels a strip needs per tap row
@@ -166,8 +176,8 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, 
     const __nv_bfloat16* xin = x + (long long)n * H * W * C + c;
     __nv_bfloat16* yout = y + (long long)n * Ho * Wo * C + c;
     if (slot < P) {
-        for (int r = 0; r < kDwRows; ++r) {
-            const int sid = (blockIdx.x * kDwRows + r) * P + slot;
+        for (int r = 0; r < rows; ++r) {
+            const int sid = (blockIdx.x * rows + r) * P + slot;
             if (sid >= n_strips) break;
             const int ho = sid / strips_w, wo0 = (sid - ho * strips_w) * S;
             float acc[S][8];
@@ -181,27 +191,41 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, 
                 const int hi = ho * STRIDE + dy - ph;
                 if (hi < 0 || hi >= H) continue;
                 const __nv_bfloat16* row = xin + (long long)hi * W * C;
-                Bf8 v[IN];                                     // kept packed (4 registers per pixel), unpacked at use
+                // input-stationary: the row segment is loaded once (packed), every pixel is unpacked ONCE and feeds all the
+                // (output j, tap dx) pairs with j*STRIDE + dx == i; the K weights of this tap row sit in registers
+                Bf8 v[IN];
+                const __nv_bfloat16* p0 = row + (long long)wi0 * C;       // may point before the row: only dereferenced in range
+                if (wi0 >= 0 && wi0 + IN <= W) {                          // interior strip: no per-pixel bounds tests
 #pragma unroll
-                for (int i = 0; i < IN; ++i) {
-                    const int wi = wi0 + i;
-                    if (wi >= 0 && wi < W) v[i] = ld8(row + (long long)wi * C);
-                    else {
+                    for (int i = 0; i < IN; ++i) v[i] = ld8(p0 + i * C);
+                } else {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) v[i].v[k] = __floats2bfloat162_rn(0.f, 0.f);
+                    for (int i = 0; i < IN; ++i) {
+                        const int wi = wi0 + i;
+                        uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                        if (wi >= 0 && wi < W) z = *reinterpret_cast<const uint4*>(p0 + i * C);
+                        *reinterpret_cast<uint4*>(&v[i]) = z;
                     }
                 }
+                float wk[K][8];
 #pragma unroll
                 for (int dx = 0; dx < K; ++dx) {
                     const float* wr = w + (dy * K + dx) * C + c;
                     const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr)), w1 = __ldg(reinterpret_cast<const float4*>(wr + 4));
-                    const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    wk[dx][0] = w0.x; wk[dx][1] = w0.y; wk[dx][2] = w0.z; wk[dx][3] = w0.w;
+                    wk[dx][4] = w1.x; wk[dx][5] = w1.y; wk[dx][6] = w1.z; wk[dx][7] = w1.w;
+                }
+#pragma unroll
+                for (int i = 0; i < IN; ++i) {
+                    float t[8];
+                    unpack8(v[i], t);
 #pragma unroll
                     for (int j = 0; j < S; ++j) {
-                        float t[8];
-                        unpack8(v[j * STRIDE + dx], t);
+                        const int dx = i - j * STRIDE;
+                        if (dx >= 0 && dx < K) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(t[k], wk[k], acc[j][k]);
+                            for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(t[k], wk[dx][k], acc[j][k]);
+                        }
                     }
                 }
             }
@@ -210,12 +234,9 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, 
                 if (wo0 + j < Wo) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) acc[j][k] = silu(acc[j][k]);
-                    const Bf8 o = pack8(acc[j]);
-                    *reinterpret_cast<Bf8*>(yout + ((long long)ho * Wo + wo0 + j) * C) = o;
-                    float rr[8];
-                    unpack8(o, rr);                                // the pool sees what the next layer sees: bf16-rounded values
+                    *reinterpret_cast<Bf8*>(yout + ((long long)ho * Wo + wo0 + j) * C) = pack8(acc[j]);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) psum[k] += rr[k];
+                    for (int k = 0; k < 8; ++k) psum[k] += acc[j][k];      // squeeze-excite pool in fp32 (before the bf16 rounding)
                 }
             }
         }
@@ -412,8 +433,11 @@ int mfb_stem_conv_bf16(const void* img, const void* w, const void* shift, void* 
     if (N < 1 || H < 1 || W < 1 || Ho < 1 || Wo < 1) return fail_status(MFB_ERR_INVALID_ARGUMENT, "stem_conv: sizes must be positive");
     if (2 * (Ho - 1) - pad_h >= H || 2 * (Wo - 1) - pad_w >= W) return fail_status(MFB_ERR_INVALID_ARGUMENT, "stem_conv: output size does not fit");
     const long long total = (long long)N * Ho * Wo;
-    stem_conv_kernel<<<grid_for(total, 128, 148 * 16), 128, 0, (cudaStream_t)stream>>>(
-        (const float*)img, (const float*)w, (const float*)shift, (__nv_bfloat16*)y, N, H, W, Ho, Wo, pad_h, pad_w);
+    StemWeights sw;                                          // HOST pointers: the weights are passed by value
+    memcpy(sw.w, w, sizeof(sw.w));
+    memcpy(sw.shift, shift, sizeof(sw.shift));
+    stem_conv_kernel<<<grid_for(total, 128, 148 * 16), 128, 0, (cudaStream_t)stream>>>((const float*)img, sw, (__nv_bfloat16*)y, N, H, W,
+                                                                                       Ho, Wo, pad_h, pad_w);
     return after_launch("stem_conv");
 }
 
@@ -430,11 +454,14 @@ int mfb_dwconv_bn_silu_bf16(const void* x, const void* w, const void* shift, voi
     const int P = 256 / G;
     const int threads = ((P * G + 31) / 32) * 32;
     const long long n_strips = (long long)Ho * ((Wo + kDwStrip - 1) / kDwStrip);
-    dim3 grid((unsigned)((n_strips + (long long)P * kDwRows - 1) / ((long long)P * kDwRows)), (unsigned)N);
+    // strips per thread: as many as possible (fewer pool atomics) while the grid keeps >= 4 waves of 2 CTAs per SM
+    long long rows = (n_strips * N) / ((long long)P * 148 * 2 * 4);
+    rows = rows < 1 ? 1 : (rows > kDwMaxRows ? kDwMaxRows : rows);
+    dim3 grid((unsigned)((n_strips + (long long)P * rows - 1) / ((long long)P * rows)), (unsigned)N);
     const size_t smem = (size_t)C * sizeof(float);
     auto go = [&](auto kern) {
         kern<<<grid, threads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const float*)w, (const float*)shift,
-                                                            (__nv_bfloat16*)y, (float*)pool, H, W, C, Ho, Wo, pad_h, pad_w);
+                                                            (__nv_bfloat16*)y, (float*)pool, H, W, C, Ho, Wo, pad_h, pad_w, (int)rows);
     };
     if (K == 3 && stride == 1) go(dwconv_kernel<3, 1>);
     else if (K == 3) go(dwconv_kernel<3, 2>);

@@ -87,8 +87,9 @@ def prepare(net):
         # --- stem: (3,3,3,32) fp32 [dy][dx][ci][co] with the BN scale folded into the weights
         s_scale, s_shift = _bn_fold(t._bn0, None, 32, dev)
         assert t._conv_stem.in_channels == 3 and t._conv_stem.out_channels == 32
-        P["stem_w"] = (t._conv_stem.weight.detach().float() * s_scale.view(-1, 1, 1, 1)).permute(2, 3, 1, 0).contiguous()
-        P["stem_shift"] = s_shift.contiguous()
+        # (host copies: the stem kernel takes its 3.5 KB of weights by value, as constant-bank operands)
+        P["stem_w"] = (t._conv_stem.weight.detach().float() * s_scale.view(-1, 1, 1, 1)).permute(2, 3, 1, 0).contiguous().cpu()
+        P["stem_shift"] = s_shift.contiguous().cpu()
         P["stem_pad"] = _static_pad(t._conv_stem)
         # --- MBConv blocks
         blocks = []

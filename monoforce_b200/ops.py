@@ -119,10 +119,12 @@ def upsample_concat_nhwc(skip, low, out_hw, c_out):
     return out
 
 
-def stem_conv(img, w, shift, pad, c_stride=32):
-    """EfficientNet stem: img (N,3,H,W) fp32 -> (N,Ho,Wo,32) bf16, 3x3 stride 2, low-side pad, BN folded, swish."""
+def stem_conv(img, w, shift, pad):
+    """EfficientNet stem: img (N,3,H,W) fp32 -> (N,Ho,Wo,32) bf16, 3x3 stride 2, low-side pad, BN folded, swish.
+    w (3,3,3,32) and shift (32,) are HOST fp32 tensors (passed to the kernel by value)."""
     _need_cuda(img, "stem_conv")
     assert img.dtype == torch.float32 and img.is_contiguous() and img.shape[1] == 3
+    assert not w.is_cuda and not shift.is_cuda and w.is_contiguous() and w.numel() == 864 and shift.numel() == 32
     N, _, H, W = img.shape
     lo, hi = pad
     Ho, Wo = conv_out_size(H, 3, 2, lo, hi), conv_out_size(W, 3, 2, lo, hi)

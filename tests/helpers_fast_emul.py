@@ -62,7 +62,7 @@ def upsample_concat_nhwc(skip, low, out_hw, c_out):
     return y
 
 
-def stem_conv(img, w, shift, pad, c_stride=32):
+def stem_conv(img, w, shift, pad):
     lo, hi = pad
     y = F.conv2d(F.pad(img, (lo, hi, lo, hi)), w.permute(3, 2, 0, 1), stride=2)
     return F.silu(y.permute(0, 2, 3, 1) + shift)

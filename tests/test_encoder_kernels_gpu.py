@@ -121,9 +121,9 @@ def test_depthwise_conv_bn_swish_and_pool(C, K, stride, pad, H, W):
     pool = torch.zeros(N, C, device=DEV)
     got = ops.dwconv_bn_silu(x.to(DEV), w.to(DEV), shift.to(DEV), K, stride, pad, pool)
     _close(got, want)
-    # the pool sums the bf16-rounded outputs: compare against that sum of the kernel's own output, then loosely vs fp32
-    assert rel_err(pool, got.float().sum((1, 2))) < 1e-4
-    assert rel_err(pool, pool_want) < 2e-2
+    # the pool sums the fp32 values before the bf16 rounding of the stored output
+    assert rel_err(pool, got.float().sum((1, 2))) < 5e-3
+    assert rel_err(pool, pool_want) < 5e-3
     again = ops.dwconv_bn_silu(x.to(DEV), w.to(DEV), shift.to(DEV), K, stride, pad, None)
     assert torch.equal(again, got)
 
@@ -148,7 +148,7 @@ def test_stem_conv_and_upsample_concat_and_cast():
     img = torch.randn(3, 3, 38, 50, generator=g)
     w = torch.randn(3, 3, 3, 32, generator=g) / 5
     shift = 0.2 * torch.randn(32, generator=g)
-    _close(ops.stem_conv(img.to(DEV), w.to(DEV), shift.to(DEV), (0, 1)), emul.stem_conv(img, w, shift, (0, 1)))
+    _close(ops.stem_conv(img.to(DEV), w, shift, (0, 1)), emul.stem_conv(img, w, shift, (0, 1)))
     for scale, Cs, Cl, Cout in ((2, 112, 320, 432), (4, 64, 256, 320), (2, 0, 256, 256), (2, 16, 24, 64)):
         low = _bf(torch.randn(2, 8, 13, Cl, generator=g))
         skip = _bf(torch.randn(2, 8 * scale, 13 * scale, Cs, generator=g)) if Cs else None
