@@ -391,13 +391,17 @@ def block_encoder(dev, steps, cfg4, peaks):
             return net(host[0].to(dev, non_blocking=True), *calib)
     n0 = _lib.kernel_launches()
     call()
-    launches = _lib.kernel_launches() - n0
+    launches = _lib.kernel_launches() - n0      # kernels of ONE forward (counted on an eager call)
+    eager_ms = timed_ms(call, 5)
+    net.fast_graph = True                 # the same launches replayed from a CUDA graph (static shapes and calibration)
     ms = timed_ms(call, max(steps // 2, 5))
     gflop_scene = 230.9 if cfg4 else 65.7          # SURVEY.md 8(a) A14 [FlopCounterMode]
     tf = 16 * gflop_scene / ms
     res = {"workload": ("BASELINE config 4 encoder: 16 scenes x 4 cams 512x512 -> 256x256 BEV" if cfg4 else
-                        "lss_cfg.yaml: 16 scenes x 4 cams 256x416 -> 128x128 BEV") + ", eval, images copied from pinned host memory",
-           "ms": ms, "scenes_per_s": 16 / (ms * 1e-3), "h2d_bytes": host[0].numel() * 4, "repo_kernel_launches": int(launches),
+                        "lss_cfg.yaml: 16 scenes x 4 cams 256x416 -> 128x128 BEV") + ", eval, all layers on repo kernels (NHWC bf16, "
+                       "CUDA-graph replay), images copied from pinned host memory inside the timed region",
+           "ms": ms, "ms_eager_launches": eager_ms, "scenes_per_s": 16 / (ms * 1e-3), "h2d_bytes": host[0].numel() * 4,
+           "repo_kernel_launches": int(launches),
            "tflops": tf, "frac_of_sustained_bf16_peak": tf / peaks["bf16"], "peak_tflops": peaks["bf16"]}
     return res, net, host, calib
 

@@ -203,7 +203,33 @@ class LiftSplatShoot(nn.Module):
         self.camencode = CamEncode(self.D, self.camC, trunk_weights=trunk_weights)
         self.bevencode = BevEncode(inC=self.camC, outC=outC)
         self.use_quickcumsum = True      # kept for attribute compatibility; the fused kernel needs neither path
-        self.fast_inference = False      # opt-in: bf16 tcgen05 path for the dense layers (eval mode only)
+        self.fast_inference = False      # opt-in: the whole network on repo kernels in NHWC bf16 (eval mode, no_grad)
+        self.fast_graph = False          # with fast_inference: replay the launches from a CUDA graph (static shapes / calibration)
+
+    def _graphed_forward(self, x, vox):
+        """The ~110 kernel launches of the inference path captured once in a CUDA graph and replayed (static shapes, static
+        calibration): removes the launch gaps that dominate at small sizes.  Re-captured when the input shape, the calibration
+        (voxel index) or any weight changes.  Outputs are copies, so they stay valid across calls."""
+        from . import encoder_fast
+        P = encoder_fast.prepare(self)            # host-side weight folding must not happen inside the capture
+        key = (tuple(x.shape), str(x.device), vox.data_ptr(), id(P))
+        g = self.__dict__.get("_mfb_graph")
+        if g is None or g["key"] != key:
+            static_x = x.detach().float().clone()
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):          # warm-up outside the capture (lazy module loading, allocator pools)
+                for _ in range(2):
+                    encoder_fast.forward(self, static_x, vox)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = encoder_fast.forward(self, static_x, vox)
+            g = {"key": key, "graph": graph, "x": static_x, "out": out, "P": P, "vox": vox}
+            self.__dict__["_mfb_graph"] = g
+        g["x"].copy_(x, non_blocking=True)
+        g["graph"].replay()
+        return {k: v.clone() for k, v in g["out"].items()}
 
     def create_frustum(self):
         """(D, fH, fW, 3) image-plane sample points (u, v, depth) - lss.py:188-202."""
@@ -290,7 +316,10 @@ class LiftSplatShoot(nn.Module):
             if int(self.nx[2]) != 1:
                 raise NotImplementedError("the fused lift-splat kernel assumes a single z voxel (zbound of lss_cfg.yaml)")
             from . import encoder_fast
-            return encoder_fast.forward(self, x, self.cached_voxel_index(rots, trans, intrins, post_rots, post_trans))
+            vox = self.cached_voxel_index(rots, trans, intrins, post_rots, post_trans)
+            if self.fast_graph:
+                return self._graphed_forward(x, vox)
+            return encoder_fast.forward(self, x, vox)
         bev = self.get_voxels(x, rots, trans, intrins, post_rots, post_trans)
         return self.bevencode(bev)
 

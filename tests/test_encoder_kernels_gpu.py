@@ -301,3 +301,28 @@ def test_terrain_and_path_postprocessing_kernels():
     ref = torch.zeros(B, T, 4, 4)
     ref[:, :, :3, 3], ref[:, :, :3, :3], ref[:, :, 3, 3] = Xs, Rs, 1.0
     assert torch.equal(poses.cpu(), ref)
+
+
+def test_fast_path_cuda_graph_replay_matches_eager_launches():
+    """fast_graph: the inference launches captured once and replayed; same numbers (up to the atomics' summation order), new
+    images are picked up, a weight update or a new calibration re-captures."""
+    net, gc, ac = _net(small_cfg)
+    a_in = [t.to(DEV) for t in make_inputs(gc, ac, 2, 2)]
+    b_in = [t.to(DEV) for t in make_inputs(gc, ac, 2, 5)]
+    eager_a, eager_b = _fast(net, a_in), _fast(net, b_in[:1] + a_in[1:])
+    net.fast_graph = True
+    g_a = _fast(net, a_in)
+    graph = net._mfb_graph["graph"]
+    g_b = _fast(net, b_in[:1] + a_in[1:])
+    assert net._mfb_graph["graph"] is graph                                   # replayed, not re-captured
+    for k in ("geom", "terrain", "diff", "friction"):
+        assert torch.allclose(g_a[k], eager_a[k], atol=2e-3) and torch.allclose(g_b[k], eager_b[k], atol=2e-3), k
+        assert not torch.allclose(g_a[k], g_b[k], atol=1e-4)
+    with torch.no_grad():
+        net.bevencode.up_diff[4].bias.add_(0.25)
+    g_c = _fast(net, a_in)
+    assert net._mfb_graph["graph"] is not graph and (g_c["diff"] - g_a["diff"]).mean().item() > 0.1
+    g_d = _fast(net, b_in)                                                     # other calibration -> other voxel index -> new graph
+    net.fast_graph = False
+    eager_d = _fast(net, b_in)
+    assert torch.allclose(g_d["terrain"], eager_d["terrain"], atol=2e-3)
