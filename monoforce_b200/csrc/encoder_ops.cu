@@ -53,22 +53,25 @@ __device__ __forceinline__ float silu(float v) {
 // ---------------------------------------------------------------------------------------------------------------
 // out[n,h,w, 0:Cs] = skip[n,h,w,:];  out[n,h,w, Cs:Cs+Cl] = bilinear(low)[n,h,w,:] (align_corners=True);  rest = 0
 // ---------------------------------------------------------------------------------------------------------------
+// IDX = unsigned (the usual case: fewer than 2^32 work items; 64-bit div / mod cost ~10x a 32-bit one) or long long
+template <typename IDX>
 __global__ void __launch_bounds__(256)
 upsample_concat_kernel(const __nv_bfloat16* __restrict__ skip, const __nv_bfloat16* __restrict__ low,
                        __nv_bfloat16* __restrict__ out, int N, int H, int W, int Cs, int Hl, int Wl, int Cl, int Cout,
                        float ry, float rx) {
-    const int G = Cout >> 3;
-    const long long total = (long long)N * H * W * G;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const IDX G = (IDX)(Cout >> 3);
+    const IDX total = (IDX)N * H * W * G;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
         const int g = (int)(i % G);
-        const long long pix = i / G;
-        const int w = (int)(pix % W);
-        const int h = (int)((pix / W) % H);
-        const int n = (int)(pix / ((long long)W * H));
+        const IDX pix = i / G;
+        const int w = (int)(pix % (IDX)W);
+        const IDX nh = pix / (IDX)W;
+        const int h = (int)(nh % (IDX)H);
+        const int n = (int)(nh / (IDX)H);
         const int c = g << 3;
         Bf8 o;
         if (c < Cs) {
-            o = ld8(skip + pix * Cs + c);
+            o = ld8(skip + (long long)pix * Cs + c);
         } else if (c < Cs + Cl) {
             const int cl = c - Cs;
             // torch upsample_bilinear2d, align_corners=True: src = dst * (in - 1) / (out - 1)
@@ -90,7 +93,7 @@ upsample_concat_kernel(const __nv_bfloat16* __restrict__ skip, const __nv_bfloat
             const float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             o = pack8(z);
         }
-        *reinterpret_cast<Bf8*>(out + pix * Cout + c) = o;
+        *reinterpret_cast<Bf8*>(out + (long long)pix * Cout + c) = o;
     }
 }
 
@@ -105,11 +108,12 @@ struct StemWeights { float w[27 * 32]; float shift[32]; };
 __global__ void __launch_bounds__(128)
 stem_conv_kernel(const float* __restrict__ img, const __grid_constant__ StemWeights sw, __nv_bfloat16* __restrict__ y, int N,
                  int H, int W, int Ho, int Wo, int ph, int pw) {
-    const long long total = (long long)N * Ho * Wo;
-    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long long)gridDim.x * blockDim.x) {
-        const int wo = (int)(pix % Wo);
-        const int ho = (int)((pix / Wo) % Ho);
-        const int n = (int)(pix / ((long long)Wo * Ho));
+    const unsigned total = (unsigned)N * Ho * Wo;            // host guarantees < 2^31 output pixels
+    for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
+        const int wo = (int)(pix % (unsigned)Wo);
+        const unsigned nh = pix / (unsigned)Wo;
+        const int ho = (int)(nh % (unsigned)Ho);
+        const int n = (int)(nh / (unsigned)Ho);
         float acc[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c] = sw.shift[c];
@@ -131,7 +135,7 @@ stem_conv_kernel(const float* __restrict__ img, const __grid_constant__ StemWeig
         }
 #pragma unroll
         for (int c = 0; c < 32; ++c) acc[c] = silu(acc[c]);
-        Bf8* dst = reinterpret_cast<Bf8*>(y + pix * 32);
+        Bf8* dst = reinterpret_cast<Bf8*>(y + (long long)pix * 32);
 #pragma unroll
         for (int q = 0; q < 4; ++q) dst[q] = pack8(acc + 8 * q);
     }
@@ -422,8 +426,12 @@ int mfb_upsample_concat_nhwc_bf16(const void* skip, const void* low, void* out, 
     if (((uintptr_t)skip | (uintptr_t)low | (uintptr_t)out) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "upsample_concat: tensors must be 16-byte aligned");
     const float ry = H > 1 ? (float)(Hl - 1) / (float)(H - 1) : 0.f, rx = W > 1 ? (float)(Wl - 1) / (float)(W - 1) : 0.f;
     const long long total = (long long)N * H * W * (C_out >> 3);
-    upsample_concat_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)skip, (const __nv_bfloat16*)low, (__nv_bfloat16*)out, N, H, W, C_skip, Hl, Wl, C_low, C_out, ry, rx);
+    if (total < (1ll << 31))
+        upsample_concat_kernel<unsigned><<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)skip, (const __nv_bfloat16*)low, (__nv_bfloat16*)out, N, H, W, C_skip, Hl, Wl, C_low, C_out, ry, rx);
+    else
+        upsample_concat_kernel<long long><<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)skip, (const __nv_bfloat16*)low, (__nv_bfloat16*)out, N, H, W, C_skip, Hl, Wl, C_low, C_out, ry, rx);
     return after_launch("upsample_concat");
 }
 
@@ -432,6 +440,7 @@ int mfb_stem_conv_bf16(const void* img, const void* w, const void* shift, void* 
     if (!img || !w || !shift || !y) return fail_status(MFB_ERR_INVALID_ARGUMENT, "stem_conv: NULL pointer");
     if (N < 1 || H < 1 || W < 1 || Ho < 1 || Wo < 1) return fail_status(MFB_ERR_INVALID_ARGUMENT, "stem_conv: sizes must be positive");
     if (2 * (Ho - 1) - pad_h >= H || 2 * (Wo - 1) - pad_w >= W) return fail_status(MFB_ERR_INVALID_ARGUMENT, "stem_conv: output size does not fit");
+    if ((long long)N * Ho * Wo >= (1ll << 31)) return fail_status(MFB_ERR_UNSUPPORTED, "stem_conv: more than 2^31 output pixels");
     const long long total = (long long)N * Ho * Wo;
     StemWeights sw;                                          // HOST pointers: the weights are passed by value
     memcpy(sw.w, w, sizeof(sw.w));

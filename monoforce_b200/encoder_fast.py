@@ -83,7 +83,7 @@ def prepare(net):
         cam, bev = net.camencode, net.bevencode
         t = cam.trunk
         dev = t._conv_stem.weight.device
-        P = {"stamp": stamp}
+        P = {"stamp": stamp, "XY": (int(net.nx[0]), int(net.nx[1]))}       # host copies: no device read on the launch path
         # --- stem: (3,3,3,32) fp32 [dy][dx][ci][co] with the BN scale folded into the weights
         s_scale, s_shift = _bn_fold(t._bn0, None, 32, dev)
         assert t._conv_stem.in_channels == 3 and t._conv_stem.out_channels == 32
@@ -214,7 +214,7 @@ def forward(net, imgs, vox):
     f16, f32 = trunk_endpoints(P, imgs.reshape(B * N, Cin, H, W).float())
     y = up_block(P["cam_up"], f16, f32, 2)
     logits = _conv(y, P["depthnet"], pad=0)                                   # (BN, fH, fW, 128) bf16, D + C used
-    X, Y = int(net.nx[0]), int(net.nx[1])
+    X, Y = P["XY"]
     bev = ops.lift_splat_bf16(logits, vox.view(-1), B, N, net.D, net.camC, X, Y)
     x1, x3 = bev_backbone(P, ops.cast_bf16(bev))
     y = up_block(P["bev_up"], x1, x3, P["bev_up_scale"])
