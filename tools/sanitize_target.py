@@ -31,6 +31,17 @@ x = inp[0].clone().requires_grad_(True)
 net(x, *inp[1:])["terrain"].sum().backward()
 with torch.no_grad():
     net.fast_inference = True
-    net(*inp)
+    out = net(*inp)        # whole inference path on repo kernels: stem, K4 (all variants incl. per-image weights, stride 2, residual,
+                           # transposed stores, fused heads), depthwise + SE, upsample/concat, bf16 lift-splat, cast, terrain post-processing
+    # map groups (one map per scene) + planner post-processing
+    cfg = DPhysConfig(robot="marv", grid_res=0.2); cfg.traj_sim_time, cfg.use_odeint = 0.05, False
+    sim = DPhysics(cfg, device=dev); sim.fused_cost = True
+    zz = torch.zeros(2, 64, 64, device=dev); cc = torch.rand(6, 5, 2, device=dev)
+    (Xs, _, Rs, _), _ = sim(zz, cc)
+    ops.path_postproc(Xs, Rs)
+    ops.terrain_postproc(out["geom"], out["diff"], out["friction"], 2)
+zz = torch.zeros(2, 64, 64, device=dev, requires_grad=True)
+(Xs, _, _, _), _ = sim(zz, cc)
+Xs.sum().backward()
 torch.cuda.synchronize()
 print("sanitize target done")
