@@ -259,6 +259,166 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Stride-1 depthwise conv through a shared-memory tile (the layers where the strip kernel above was latency-bound: every
+// thread waited for its own tap-row loads before its FMAs).  A CTA owns TH x TW output pixels x 32 channels of one image:
+// the (TH + K - 1) x (TW + K - 1) input patch is brought in with cp.async (16 bytes per request, zero-filled outside the
+// image = the conv's padding), then each thread computes one 4-pixel strip x 8 channels from shared memory.  Several CTAs
+// per SM overlap one CTA's loads with another's FMAs.  Pixel pitch in shared memory = 64 + 16 bytes: conflict-free LDS.128.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kDwSlab = 32;                      // channels per CTA
+constexpr int kDwPitch = kDwSlab * 2 + 16;       // bytes per staged pixel
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;               // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gmem_src), "r"(sz) : "memory");
+}
+
+constexpr int kDwChunk = 16;                     // spatial tiles of one (image, channel slab) a CTA works through before it flushes its pool sums
+
+template <int K>
+__global__ void __launch_bounds__(256, 2)
+dwconv_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
+                   __nv_bfloat16* __restrict__ y, float* __restrict__ pool, int N, int H, int W, int C, int ph, int pw, int TW,
+                   int TH) {
+    // Persistent and double-buffered: a CTA walks work units = (image, 32-channel slab, chunk of up to 16 spatial tiles); the
+    // cp.async requests of tile i+1 are in flight while tile i is computed, and the squeeze-excite partial sums stay in
+    // registers for a whole unit (one shuffle-reduce + one atomic per channel per unit instead of per tile).
+    extern __shared__ __align__(16) unsigned char dw_smem[];
+    constexpr int S = kDwStrip, IN = K + S - 1;
+    float* pool_s = reinterpret_cast<float*>(dw_smem);                 // [32]
+    const int TWI = TW + K - 1, THI = TH + K - 1;
+    const int tile_bytes = THI * TWI * kDwPitch;
+    unsigned char* const buf0 = dw_smem + 128;
+    const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
+    const int sp_tiles = tiles_w * tiles_h;
+    const int chunks = (sp_tiles + kDwChunk - 1) / kDwChunk;
+    const int slabs = (C + kDwSlab - 1) / kDwSlab;
+    const int units = N * slabs * chunks;
+
+    // cp.async staging of spatial tile q of (image n, slab): thread i handles patch entries i, i + 256, ... (entry = pixel * 4 + group)
+    const int e_pix0 = threadIdx.x >> 2, e_g = threadIdx.x & 3;
+    const int e_iy0 = e_pix0 / TWI, e_ix0 = e_pix0 - e_iy0 * TWI;     // one division per kernel, then incremental
+    const int step_iy = 64 / TWI, step_ix = 64 - step_iy * TWI;
+    auto stage = [&](int n, int slab, int q, unsigned char* tile) {
+        const int h0 = (q / tiles_w) * TH, w0 = (q % tiles_w) * TW, c0 = slab * kDwSlab;
+        const bool gok = e_g < min(4, (C - c0) >> 3);
+        const __nv_bfloat16* xin = x + (long long)n * H * W * C + c0 + e_g * 8;
+        int ix = e_ix0, iy = e_iy0;
+        for (int pxy = e_pix0; pxy < THI * TWI; pxy += 64) {
+            const int hi = h0 + iy - ph, wi = w0 + ix - pw;
+            const bool ok = gok && hi >= 0 && hi < H && wi >= 0 && wi < W;
+            cp_async16(tile + pxy * kDwPitch + e_g * 16, ok ? xin + ((long long)hi * W + wi) * C : xin, ok);
+            ix += step_ix; iy += step_iy;
+            if (ix >= TWI) { ix -= TWI; ++iy; }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // thread -> (strip, channel group): 4 groups x (TW/4) strips x TH rows = 256 threads
+    const int g = threadIdx.x & 3;
+    const int sidx = threadIdx.x >> 2;
+    const int sw = sidx % (TW / S), sh = sidx / (TW / S);
+
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int n = u / (slabs * chunks), r = u - n * slabs * chunks;
+        const int slab = r / chunks, q0 = (r - slab * chunks) * kDwChunk;
+        const int q1 = min(q0 + kDwChunk, sp_tiles);
+        const int c0 = slab * kDwSlab;
+        const int gmax = min(4, (C - c0) >> 3);
+        const int c = c0 + g * 8;
+        const bool live = g < gmax && sh < TH;
+        float sh8[8], psum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (live) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + c)), s1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
+            sh8[0] = s0.x; sh8[1] = s0.y; sh8[2] = s0.z; sh8[3] = s0.w; sh8[4] = s1.x; sh8[5] = s1.y; sh8[6] = s1.z; sh8[7] = s1.w;
+        }
+        __syncthreads();                                                    // the previous unit is done with both buffers and pool_s
+        if (threadIdx.x < 32) pool_s[threadIdx.x] = 0.f;
+        stage(n, slab, q0, buf0);
+        for (int q = q0, it = 0; q < q1; ++q, ++it) {
+            unsigned char* const tile = buf0 + (it & 1) * tile_bytes;
+            if (q + 1 < q1) {
+                stage(n, slab, q + 1, buf0 + ((it + 1) & 1) * tile_bytes);      // prefetch the next tile into the other buffer
+                asm volatile("cp.async.wait_group 1;" ::: "memory");            // ... and wait for the current one only
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
+            if (live) {
+                const int h0 = (q / tiles_w) * TH, w0 = (q % tiles_w) * TW;
+                float acc[S][8];
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[j][k] = sh8[k];
+#pragma unroll
+                for (int dy = 0; dy < K; ++dy) {
+                    const unsigned char* row = tile + ((sh + dy) * TWI + sw * S) * kDwPitch + g * 16;
+                    float wk[K][8];
+#pragma unroll
+                    for (int dx = 0; dx < K; ++dx) {
+                        const float* wr = w + (dy * K + dx) * C + c;
+                        const float4 w0v = __ldg(reinterpret_cast<const float4*>(wr)), w1v = __ldg(reinterpret_cast<const float4*>(wr + 4));
+                        wk[dx][0] = w0v.x; wk[dx][1] = w0v.y; wk[dx][2] = w0v.z; wk[dx][3] = w0v.w;
+                        wk[dx][4] = w1v.x; wk[dx][5] = w1v.y; wk[dx][6] = w1v.z; wk[dx][7] = w1v.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < IN; ++i) {
+                        float tv[8];
+                        unpack8(*reinterpret_cast<const Bf8*>(row + i * kDwPitch), tv);
+#pragma unroll
+                        for (int j = 0; j < S; ++j) {
+                            const int dx = i - j;
+                            if (dx >= 0 && dx < K) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(tv[k], wk[dx][k], acc[j][k]);
+                            }
+                        }
+                    }
+                }
+                const int ho = h0 + sh;
+                if (ho < H) {
+                    __nv_bfloat16* yout = y + (((long long)n * H + ho) * W) * C + c;
+#pragma unroll
+                    for (int j = 0; j < S; ++j) {
+                        const int wo = w0 + sw * S + j;
+                        if (wo < W) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) acc[j][k] = silu(acc[j][k]);
+                            *reinterpret_cast<Bf8*>(yout + (long long)wo * C) = pack8(acc[j]);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) psum[k] += acc[j][k];
+                        }
+                    }
+                }
+            }
+            __syncthreads();              // everyone is done with this tile's buffer (it is the prefetch target of the next iteration)
+        }
+        if (pool) {
+            // lanes l, l+4, l+8 ... of a warp hold the same channel group: fold them with xor-shuffles, then 8 shared atomics per group
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                float v = psum[k];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                psum[k] = v;
+            }
+            if ((threadIdx.x & 31) < 4 && g < gmax) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) atomicAdd(pool_s + g * 8 + k, psum[k]);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32 && c0 + (int)threadIdx.x < C) {
+                const float v = pool_s[threadIdx.x];
+                if (v != 0.f) atomicAdd(pool + (long long)n * C + c0 + threadIdx.x, v);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // squeeze-excite folded into per-image projection weights, two launches:
 //   se_mlp   grid N:  m = pool[n,:] * inv_hw;  r = swish(Wr m + br) (Sq);  s = sigmoid(We r + be) (C);  pool[n,:] <- s
 //   se_scale grid (ceil(Cout / kSeRows), N):  out[n,co,c] = proj[co,c] * s[n,c]
@@ -458,6 +618,25 @@ int mfb_dwconv_bn_silu_bf16(const void* x, const void* w, const void* shift, voi
     if (K != 3 && K != 5) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: kernel size must be 3 or 5");
     if (stride != 1 && stride != 2) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: stride must be 1 or 2");
     if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)w | (uintptr_t)shift) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "dwconv: tensors must be 16-byte aligned");
+    if (stride == 1 && Ho == H && Wo == W) {
+        // stride 1 ("same"): shared-memory tile kernel; 32-wide tiles unless the map is narrower
+        const int TW = W > 16 ? 32 : 16, TH = 256 / TW;                 // 4 groups x (TW/4) strips x TH rows = 256 threads
+        const long long sp = (long long)((W + TW - 1) / TW) * ((H + TH - 1) / TH);
+        const long long tiles = ((sp + kDwChunk - 1) / kDwChunk) * ((C + kDwSlab - 1) / kDwSlab) * N;     // work units
+        if (tiles >= (1ll << 31)) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: too many tiles");
+        const long long resident = 148ll * 2;                          // persistent: 2 CTAs per SM
+        dim3 grid((unsigned)(tiles < resident ? tiles : resident));
+        const size_t smem = 128 + 2 * (size_t)(TH + K - 1) * (TW + K - 1) * kDwPitch;    // two tile buffers
+        auto go = [&](auto kern) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+            kern<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const float*)w, (const float*)shift,
+                                                           (__nv_bfloat16*)y, (float*)pool, N, H, W, C, pad_h, pad_w, TW, TH);
+            return true;
+        };
+        if (!(K == 3 ? go(dwconv_tile_kernel<3>) : go(dwconv_tile_kernel<5>)))
+            return fail_status(MFB_ERR_CUDA, "dwconv: cudaFuncSetAttribute failed");
+        return after_launch("dwconv (tile)");
+    }
     const int G = C >> 3;
     if (G > 256) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: at most 2048 channels");
     const int P = 256 / G;
