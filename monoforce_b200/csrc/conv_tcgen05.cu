@@ -50,6 +50,7 @@ static int launch_v(const CUtensorMap& mx, const CUtensorMap& mw, const Params& 
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return fail_status(MFB_ERR_CUDA, "conv: cudaFuncSetAttribute failed");
     const long long tiles = (long long)p.tiles_w * p.tiles_h * p.N * ((p.Cout + BLOCK_N - 1) / BLOCK_N);
+    if (tiles >= (1ll << 31)) return fail_status(MFB_ERR_UNSUPPORTED, "conv: more than 2^31 tiles");
     const long long resident = 2ll * sm_count();             // persistent: 2 CTAs per SM walk the tiles
     dim3 grid((unsigned)(tiles < resident ? tiles : resident));
     kern<<<grid, kThreads, smem, st>>>(mx, mw, p);

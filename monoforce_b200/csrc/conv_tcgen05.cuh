@@ -197,7 +197,9 @@ template <int BLOCK_N, int ACT, bool HEAD, int kStages, bool XPOSE>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);    // SWIZZLE_128B needs 1024-B alignment
+    // SWIZZLE_128B needs 1024-B alignment.  The offset is added to the __shared__ array itself (not to an integer cast of it), so
+    // that the compiler keeps the address space and emits LDS / STS instead of generic LD / ST for the epilogue's accesses.
+    uint8_t* smem = smem_raw + ((1024u - (s_addr(smem_raw) & 1023u)) & 1023u);
     using S = Smem<BLOCK_N, kStages, XPOSE>;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::kBarrierOffset);
     uint64_t* empty = full + kStages;
@@ -208,7 +210,7 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_blocks = (p.Cout + BLOCK_N - 1) / BLOCK_N;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
-    const long long total = (long long)tiles_per_img * p.N * n_blocks;
+    const unsigned total = (unsigned)tiles_per_img * p.N * n_blocks;     // host guarantees < 2^31: 32-bit div / mod on the tile walk
     // Cin need not be a multiple of 64: the last chunk's channels beyond Cin are outside the tensor map's extent, which the
     // TMA unit fills with zeros (for the weights too, whose rows are KH*KW*Cin long), so they add nothing to the sum
     const int chunks_per_tap = (p.Cin + kBlockK - 1) / kBlockK;
@@ -243,10 +245,11 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         if (lane == 0) {
             // ===== TMA producer =====
             uint32_t it = 0;
-            for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-                const int nb = (int)(t % n_blocks);
-                const long long pt = t / n_blocks;
-                const int tw = (int)(pt % p.tiles_w), th = (int)((pt / p.tiles_w) % p.tiles_h), n = (int)(pt / tiles_per_img);
+            for (unsigned t = blockIdx.x; t < total; t += gridDim.x) {
+                const unsigned pt = t / (unsigned)n_blocks;
+                const int nb = (int)(t - pt * n_blocks);
+                const unsigned n_ = pt / (unsigned)tiles_per_img, rem = pt - n_ * tiles_per_img;
+                const int th = (int)(rem / (unsigned)p.tiles_w), tw = (int)(rem - th * p.tiles_w), n = (int)n_;
                 const int w0 = tw * kTileW, h0 = th * kTileH, n0 = nb * BLOCK_N;
                 for (int i = 0; i < k_iters; ++i, ++it) {
                     const int s = it % kStages;
@@ -269,7 +272,7 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             // ===== MMA issuer (one thread) =====
             constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
             uint32_t it = 0, lt = 0;
-            for (long long t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+            for (unsigned t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
                 const uint32_t as = lt & 1;
                 mbar_wait(acc_empty + as, ((lt >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
                 tc_fence_after();
@@ -301,10 +304,11 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         float* head_part = reinterpret_cast<float*>(tmem_slot + 4);     // [kBlockM] partial head dots of the upper column half
         uint8_t* const xbuf = smem + S::kXposeOffset + (warp - 2) * 32 * kXposePitch;   // this warp's transpose buffer (XPOSE)
         uint32_t lt = 0;
-        for (long long t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
-            const int nb = (int)(t % n_blocks);
-            const long long pt = t / n_blocks;
-            const int tw = (int)(pt % p.tiles_w), th = (int)((pt / p.tiles_w) % p.tiles_h), n = (int)(pt / tiles_per_img);
+        for (unsigned t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+            const unsigned pt = t / (unsigned)n_blocks;
+            const int nb = (int)(t - pt * n_blocks);
+            const unsigned n_ = pt / (unsigned)tiles_per_img, rem = pt - n_ * tiles_per_img;
+            const int th = (int)(rem / (unsigned)p.tiles_w), tw = (int)(rem - th * p.tiles_w), n = (int)n_;
             const int n0 = nb * BLOCK_N;
             const int h = th * kTileH + hh, w = tw * kTileW + ww;
             const bool in_image = (h < p.Ho) && (w < p.Wo);
