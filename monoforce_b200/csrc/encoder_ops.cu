@@ -41,6 +41,15 @@ __device__ __forceinline__ Bf8 pack8(const float* f) {
     for (int i = 0; i < 4; ++i) b.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
     return b;
 }
+// acc[0..7] += t[0..7] * w[0..7] as four packed fma.rn.f32x2 (FFMA2: two FMAs per issue slot on sm_100a; the depthwise kernels
+// are issue-bound, and the bf16 unpack already leaves channel pairs in adjacent registers)
+__device__ __forceinline__ void fma8(float* acc, const float* t, const float* w) {
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+        const float2 r = __ffma2_rn(make_float2(t[k], t[k + 1]), make_float2(w[k], w[k + 1]), make_float2(acc[k], acc[k + 1]));
+        acc[k] = r.x; acc[k + 1] = r.y;
+    }
+}
 __device__ __forceinline__ Bf8 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const Bf8*>(p); }
 // x sigmoid(x) = x/2 (1 + tanh(x/2)): one SFU op + 2 FMA-class instructions (tanh.approx: 2^-11 relative, below bf16 rounding)
 __device__ __forceinline__ float silu(float v) {
@@ -227,8 +236,7 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, 
                     for (int j = 0; j < S; ++j) {
                         const int dx = i - j * STRIDE;
                         if (dx >= 0 && dx < K) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(t[k], wk[dx][k], acc[j][k]);
+                            fma8(acc[j], t, wk[dx]);
                         }
                     }
                 }
@@ -371,8 +379,7 @@ dwconv_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict_
                         for (int j = 0; j < S; ++j) {
                             const int dx = i - j;
                             if (dx >= 0 && dx < K) {
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(tv[k], wk[dx][k], acc[j][k]);
+fma8(acc[j], tv, wk[dx]);
                             }
                         }
                     }
