@@ -1,4 +1,5 @@
 // Host side of K4 (conv_tcgen05.cuh): TMA tensor maps + launch, exported through the C ABI.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -135,6 +136,7 @@ extern "C" int mfb_conv2d_bf16(const mfb_conv_desc* d, const void* x, const void
     p.tiles_w = (d->Wo + kTileW - 1) / kTileW;
     p.tiles_h = (d->Ho + kTileH - 1) / kTileH;
     p.per_image_w = d->per_image_weights ? 1 : 0;
+    { const char* dbg = getenv("MFB_CONV_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     p.y = (__nv_bfloat16*)y; p.res = (const __nv_bfloat16*)residual;
     p.scale = (const float*)scale; p.shift = (const float*)shift;
     p.head_out = head ? (float*)head_out : nullptr;

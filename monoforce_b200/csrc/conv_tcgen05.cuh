@@ -52,6 +52,7 @@ struct Params {
     int KH, KW, stride, pad_h, pad_w, act;
     int tiles_w, tiles_h;
     int per_image_w;               // weights are (N, Cout, KH*KW*Cin): the CTA's image selects the matrix
+    int debug;                     // development only (MFB_CONV_DEBUG): 1 = skip the global stores, 2 = skip the TMEM loads, 4 = producer/MMA idle
     __nv_bfloat16* y;              // nullptr in head mode
     const __nv_bfloat16* res;      // residual added before the activation, or nullptr
     const float* scale;
@@ -348,7 +349,8 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 for (int c = c_lo; c < c_lo + kColsPerWarp; c += 32) {
                     if (n0 + c >= p.Cout) break;              // warp-uniform: nothing but padding columns left
                     uint32_t r[32];
-                    tmem_ld32(tmem_acc + c, r);
+                    if (!(p.debug & 2)) tmem_ld32(tmem_acc + c, r);
+                    else { for (int j = 0; j < 32; ++j) r[j] = lane + j; }
                     if (in_image) {
 #pragma unroll
                         for (int g8 = 0; g8 < 4; ++g8) {
@@ -388,7 +390,7 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                             const int row = 8 * k + (lane >> 2);             // row of this warp's 32 accumulator rows
                             const int mm = q * 32 + row;
                             const int h2 = th * kTileH + mm / kTileW, w2 = tw * kTileW + (mm % kTileW);
-                            if (h2 < p.Ho && w2 < p.Wo && co < p.Cout) {
+                            if (h2 < p.Ho && w2 < p.Wo && co < p.Cout && !(p.debug & 1)) {
                                 const uint4 val = *reinterpret_cast<const uint4*>(xbuf + row * kXposePitch + part * 16);
                                 *reinterpret_cast<uint4*>(p.y + (((long long)n * p.Ho + h2) * p.Wo + w2) * p.Cout + co) = val;
                             }

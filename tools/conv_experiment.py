@@ -1,0 +1,27 @@
+"""Where does a memory-bound K4 layer spend its time?  Times MBConv block-1 expand (64 x 256 x 256 x 16 -> 96, 1x1, SiLU) and a few
+other shapes; run under different MFB_CONV_DEBUG values (development switch in the kernel)."""
+import os, sys
+_R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [_R, os.path.join(_R, "tests")]
+import torch
+from monoforce_b200 import ops
+
+def timed(fn, n=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+dev = "cuda"
+for name, (N, H, W, Cin, Cout, act) in {"b1_expand 16->96 @256": (64, 256, 256, 16, 96, ops.ACT_SILU), "b2_expand 24->144 @128": (64, 128, 128, 24, 144, ops.ACT_SILU),
+                                      "64->96 @256 (full K chunk)": (64, 256, 256, 64, 96, ops.ACT_SILU), "16->128 @256": (64, 256, 256, 16, 128, ops.ACT_SILU),
+                                      "b0_project 32->16 @256": (64, 256, 256, 32, 16, ops.ACT_NONE)}.items():
+    x = torch.randn(N, H, W, Cin, device=dev).to(torch.bfloat16)
+    w = (torch.randn(Cout, 1, 1, Cin, device=dev) * 0.1).to(torch.bfloat16)
+    sc, sh = torch.ones(Cout, device=dev), torch.zeros(Cout, device=dev)
+    ms = timed(lambda: ops.conv2d_nhwc(x, w, sc, sh, act))
+    mb = (x.numel() + N * H * W * Cout) * 2 / 1e6
+    print(f"debug={os.environ.get('MFB_CONV_DEBUG', '0')}  {name:32s} {ms * 1e3:8.1f} us   {mb:7.0f} MB  -> {mb / ms / 1e3:6.2f} TB/s", flush=True)
