@@ -169,7 +169,7 @@ int mfb_lift_splat_forward_bf16(const void* logits, int row_stride, const void* 
  *   squeeze-excite block; zero it first).  w (K*K, C) fp32, shift (C,) fp32.
  * mfb_se_fold_bf16: s = sigmoid(W_expand swish(W_reduce (pool * inv_hw) + b_reduce) + b_expand) per image and
  *   out_w[n,co,c] = proj_w[co,c] * s[c]: the excite scale folded into that image's projection matrix (consumed by
- *   mfb_conv2d_bf16 with per_image_weights).  w_reduce (Sq,C_se), w_expand (C_se,Sq) fp32; channels [C_se, C) are padding.
+ *   mfb_conv2d_bf16 with per_image_weights).  w_reduce (Sq,C_se) and the TRANSPOSE of w_expand, also (Sq,C_se), fp32; channels [C_se, C) are padding.
  *   `pool` (N,C) is OVERWRITTEN with the excite scale s (two launches: the MLP once per image, then the scaling).
  * mfb_cast_f32_to_bf16: n scalars (multiple of 8). */
 int mfb_upsample_concat_nhwc_bf16(const void* skip, const void* low, void* out, int N, int H, int W, int C_skip, int Hl,

@@ -429,7 +429,7 @@ fma8(acc[j], tv, wk[dx]);
 // squeeze-excite folded into per-image projection weights, two launches:
 //   se_mlp   grid N:  m = pool[n,:] * inv_hw;  r = swish(Wr m + br) (Sq);  s = sigmoid(We r + be) (C);  pool[n,:] <- s
 //   se_scale grid (ceil(Cout / kSeRows), N):  out[n,co,c] = proj[co,c] * s[n,c]
-// Wr (Sq, Cse), We (Cse, Sq): Cse = the block's real channel count; channels [Cse, C) are padding: s = 0 there.
+// Wr (Sq, Cse), We TRANSPOSED (Sq, Cse): Cse = the block's real channel count; channels [Cse, C) are padding: s = 0 there.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSeRows = 16;
 constexpr int kSeMaxC = 1280, kSeMaxSq = 64;
@@ -454,7 +454,7 @@ se_mlp_kernel(float* __restrict__ pool, float inv_hw, const float* __restrict__ 
         float v = 0.f;
         if (c < Cse) {
             float a = __ldg(be + c);
-            for (int q = 0; q < Sq; ++q) a = fmaf(__ldg(We + (long long)c * Sq + q), r[q], a);
+            for (int q = 0; q < Sq; ++q) a = fmaf(__ldg(We + (long long)q * Cse + c), r[q], a);      // We^T (Sq, Cse): coalesced over c
             v = __fdividef(1.f, 1.f + __expf(-a));
         }
         row[c] = v;

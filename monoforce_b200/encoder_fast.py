@@ -122,7 +122,7 @@ def prepare(net):
             b["dw_shift"] = d_shift.contiguous()
             sq = blk._se_reduce.out_channels
             b["se"] = (blk._se_reduce.weight.detach().float().view(sq, oup).contiguous(), blk._se_reduce.bias.detach().float().contiguous(),
-                       blk._se_expand.weight.detach().float().view(oup, sq).contiguous(), blk._se_expand.bias.detach().float().contiguous())
+                       blk._se_expand.weight.detach().float().view(oup, sq).t().contiguous(), blk._se_expand.bias.detach().float().contiguous())
             b["proj"] = _conv_spec(blk._project_conv, blk._bn2, ops.ACT_NONE)
             b["proj_w2d"] = b["proj"]["w"].view(blk._project_conv.out_channels, oup).contiguous()
             blocks.append(b)

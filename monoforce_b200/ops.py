@@ -150,8 +150,9 @@ def dwconv_bn_silu(x, w, shift, K, stride, pad, pool=None):
     return y
 
 
-def se_fold(pool, inv_hw, w_reduce, b_reduce, w_expand, b_expand, proj_w):
-    """Per-image projection matrices with the squeeze-excite scale folded in: (N, Cout, 1, 1, C) bf16."""
+def se_fold(pool, inv_hw, w_reduce, b_reduce, w_expand_t, b_expand, proj_w):
+    """Per-image projection matrices with the squeeze-excite scale folded in: (N, Cout, 1, 1, C) bf16.  w_reduce (Sq, C) and
+    w_expand_t (Sq, C) = the TRANSPOSE of the expand weights (coalesced reads); `pool` is overwritten with the excite scale."""
     _need_cuda(pool, "se_fold")
     N, Cc = pool.shape
     Cout = proj_w.shape[0]
@@ -159,7 +160,8 @@ def se_fold(pool, inv_hw, w_reduce, b_reduce, w_expand, b_expand, proj_w):
     out = torch.empty(N, Cout, 1, 1, Cc, dtype=torch.bfloat16, device=pool.device)
     lib = _lib.load()
     with torch.cuda.device(pool.device):
-        _lib.check(lib.mfb_se_fold_bf16(_p(pool), float(inv_hw), _p(w_reduce), _p(b_reduce), _p(w_expand), _p(b_expand), _p(proj_w),
+        assert w_expand_t.shape == w_reduce.shape
+        _lib.check(lib.mfb_se_fold_bf16(_p(pool), float(inv_hw), _p(w_reduce), _p(b_reduce), _p(w_expand_t), _p(b_expand), _p(proj_w),
                                         _p(out), N, Cc, Cse, Sq, Cout, _stream(pool.device)), "mfb_se_fold_bf16")
     return out
 

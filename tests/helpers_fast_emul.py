@@ -79,10 +79,10 @@ def dwconv_bn_silu(x, w, shift, K, stride, pad, pool=None):
     return y
 
 
-def se_fold(pool, inv_hw, w_reduce, b_reduce, w_expand, b_expand, proj_w):
+def se_fold(pool, inv_hw, w_reduce, b_reduce, w_expand_t, b_expand, proj_w):
     m = pool * inv_hw
     r = F.silu(m @ w_reduce.t() + b_reduce)
-    s = torch.sigmoid(r @ w_expand.t() + b_expand)                      # (N, C)
+    s = torch.sigmoid(r @ w_expand_t + b_expand)                        # (N, C); w_expand_t (Sq, C)
     return (proj_w.float().unsqueeze(0) * s.unsqueeze(1)).view(pool.shape[0], proj_w.shape[0], 1, 1, proj_w.shape[1])
 
 

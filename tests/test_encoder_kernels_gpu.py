@@ -134,7 +134,7 @@ def test_squeeze_excite_fold_into_projection_weights():
     for N, C, Sq, Cout in ((4, 32, 8, 16), (3, 1152, 48, 320), (2, 240, 10, 80)):
         pool = torch.rand(N, C, generator=g) * 50
         wr, br = torch.randn(Sq, C, generator=g) / C ** 0.5, 0.1 * torch.randn(Sq, generator=g)
-        we, be = torch.randn(C, Sq, generator=g) / Sq ** 0.5, 0.1 * torch.randn(C, generator=g)
+        we, be = torch.randn(Sq, C, generator=g) / Sq ** 0.5, 0.1 * torch.randn(C, generator=g)      # expand weights, transposed
         proj = _bf(torch.randn(Cout, C, generator=g))
         want = emul.se_fold(pool, 1 / 49.0, wr, br, we, be, proj)
         got = ops.se_fold(pool.to(DEV), 1 / 49.0, wr.to(DEV), br.to(DEV), we.to(DEV), be.to(DEV), proj.to(DEV))
@@ -326,3 +326,58 @@ def test_fast_path_cuda_graph_replay_matches_eager_launches():
     net.fast_graph = False
     eager_d = _fast(net, b_in)
     assert torch.allclose(g_d["terrain"], eager_d["terrain"], atol=2e-3)
+
+
+def test_conv2d_random_shapes_fuzz():
+    """40 random small problems (any Cin / Cout multiple of 8, K in 1..7, stride 1 / 2, every low-side padding that fits,
+    ragged spatial sizes down to 1 x 1, all activations, residual on / off, per-image weights on / off) against the fp32 statement:
+    the tile walk, TMA zero fill (spatial and channel), the transposed / direct store paths and the 64 / 128-column variants all
+    get hit by construction."""
+    from monoforce_b200 import ops
+    rng = np.random.RandomState(1234)
+    for case in range(40):
+        K = int(rng.choice([1, 1, 2, 3, 3, 5, 7]))
+        stride = int(rng.choice([1, 1, 2]))
+        pad = int(rng.randint(0, K))
+        Cin, Cout = 8 * int(rng.randint(1, 24)), 8 * int(rng.randint(1, 24))
+        N = int(rng.randint(1, 4))
+        H, W = int(rng.randint(max(1, K - 2 * pad), 40)), int(rng.randint(max(1, K - 2 * pad), 40))
+        Ho, Wo = emul.conv_out_size(H, K, stride, pad, pad), emul.conv_out_size(W, K, stride, pad, pad)
+        if Ho < 1 or Wo < 1:
+            continue
+        act = int(rng.randint(0, 4))
+        per_image, with_res = bool(rng.randint(0, 2)) and K == 1, bool(rng.randint(0, 2))
+        g = torch.Generator().manual_seed(case)
+        x = _bf(torch.randn(N, H, W, Cin, generator=g))
+        w = _bf(torch.randn(*((N,) if per_image else ()), Cout, K, K, Cin, generator=g) / np.sqrt(K * K * Cin))
+        scale, shift = 0.5 + torch.rand(Cout, generator=g), 0.2 * torch.randn(Cout, generator=g)
+        res = _bf(torch.randn(N, Ho, Wo, Cout, generator=g)) if with_res else None
+        want = emul.conv2d_nhwc(x, w, scale, shift, act, stride=stride, pad=(pad, pad), out_hw=(Ho, Wo), residual=res)
+        got = ops.conv2d_nhwc(x.to(DEV), w.to(DEV), scale.to(DEV), shift.to(DEV), act, stride=stride, pad=(pad, pad), out_hw=(Ho, Wo),
+                              residual=None if res is None else res.to(DEV))
+        err = (got.float().cpu() - want).abs()
+        ok = err.max() <= 3e-2 * want.abs().max() + 1e-3
+        assert ok, (case, dict(K=K, stride=stride, pad=pad, Cin=Cin, Cout=Cout, N=N, H=H, W=W, act=act, per_image=per_image, res=with_res),
+                    err.max().item(), want.abs().max().item())
+
+
+def test_depthwise_random_shapes_fuzz():
+    from monoforce_b200 import ops
+    rng = np.random.RandomState(99)
+    for case in range(24):
+        K = int(rng.choice([3, 5]))
+        stride = int(rng.choice([1, 2]))
+        pad = ((K - 1) // 2, (K - 1) // 2) if stride == 1 else ((0, 1) if K == 3 else (1, 2))
+        C = 8 * int(rng.randint(1, 40))
+        N, H, W = int(rng.randint(1, 4)), int(rng.randint(K, 45)), int(rng.randint(K, 45))
+        g = torch.Generator().manual_seed(1000 + case)
+        x = _bf(torch.randn(N, H, W, C, generator=g))
+        w, shift = torch.randn(K * K, C, generator=g) / K, 0.3 * torch.randn(C, generator=g)
+        pool_want = torch.zeros(N, C)
+        want = emul.dwconv_bn_silu(x, w, shift, K, stride, pad, pool_want)
+        pool = torch.zeros(N, C, device=DEV)
+        got = ops.dwconv_bn_silu(x.to(DEV), w.to(DEV), shift.to(DEV), K, stride, pad, pool)
+        assert got.shape == want.shape, (case, got.shape, want.shape)
+        err = (got.float().cpu() - want).abs()
+        assert err.max() <= 2e-2 * want.abs().max() + 1e-3, (case, K, stride, C, N, H, W, err.max().item())
+        assert rel_err(pool, pool_want) < 1e-2, (case, K, stride, C, N, H, W)
