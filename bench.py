@@ -524,6 +524,7 @@ def main():
             states_gt = tuple(s.clone() for s in states_gt)
         z = d["z0"].to(dev).unsqueeze(0).requires_grad_(True)
         fr = d["fr0"].to(dev).unsqueeze(0).requires_grad_(True)
+        coll_events = [] if world > 1 else None      # CUDA events around the exposed collective tail of every step
         costs_all = torch.empty(world * B, device=dev)
         # the kernel writes this rank's costs straight into its slice of the gather buffer (in-place all-gather)
         sim.cost_buffer = costs_all[rank * B:(rank + 1) * B]
@@ -538,10 +539,16 @@ def main():
             loss = physics_loss(states, states_gt, ts, ts, 0.9)
             loss.backward()
             if world > 1:
+                if coll_events is not None:
+                    e0, e1 = _ev(), _ev()
+                    e0.record()
                 allreduce_map_grads(z.grad, fr.grad)           # both 256 KiB maps: one flat in-place all-reduce
                 work.wait()
+                if coll_events is not None:
+                    e1.record()
+                    coll_events.append((e0, e1))
             return loss
-        return step, sim, dict(d=d, controls=controls, ts=ts, states_gt=states_gt, z=z, fr=fr, costs_all=costs_all)
+        return step, sim, dict(d=d, controls=controls, ts=ts, states_gt=states_gt, z=z, fr=fr, costs_all=costs_all, coll=coll_events)
 
     B = args.traj_per_gpu
     step, sim, J = make_job(B, seed=rank)        # each rank owns a different shard of control sequences
@@ -564,6 +571,13 @@ def main():
     barrier()
     launches = _lib.kernel_launches() - n0
     clocks = sampler.stop()
+    coll_ms = None
+    if J["coll"]:
+        tail = [a.elapsed_time(b) for a, b in J["coll"][-args.steps:]]
+        mine = sum(tail) / len(tail)
+        (hi,), (neg_lo,) = max_over_ranks(mine), max_over_ranks(-mine)
+        # the rank that arrives last waits least: min over ranks ~ the collectives themselves, max - min ~ skew between ranks
+        coll_ms = {"max_over_ranks": hi, "min_over_ranks": -neg_lo}
     ms_step = t_a.elapsed_time(t_b) / args.steps
     fwd_t = [a.elapsed_time(b_) for n, a, b_ in sim.timings if n == "forward"]
     bwd_t = [a.elapsed_time(b_) for n, a, b_ in sim.timings if n == "backward"]
@@ -722,6 +736,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "cpu_baseline": cpu,
+            "collective_tail_ms": coll_ms,
             "strong_scaling": strong,
             "cfg5": cfg5,
             **extras,
