@@ -17,7 +17,8 @@
 // Tiling: one CTA = 128 output pixels (TH x TW = 8 x 16 patch of one image) x BLOCK_N output channels.
 // The K loop runs over (tap, 64-channel chunk): for each, TMA loads the SHIFTED (and for stride 2: element-strided)
 // activation patch as a 4-D box {64 ch, TW*s, TH*s, 1} with traversal strides {1,s,s,1} (out-of-image rows/columns are
-// zero-filled by the TMA unit == the conv's zero padding) and the matching weight slab {64, BLOCK_N}; both land in
+// zero-filled by the TMA unit == the conv's zero padding; so are the channels beyond Cin when Cin % 64 != 0) and the matching
+// weight slab {64, BLOCK_N}; both land in
 // 128-byte-swizzled K-major shared tiles, the canonical UMMA operand layout, so no im2col buffer ever exists.
 // Persistent CTAs (2 per SM) walk the tiles; two TMEM accumulators overlap one tile's epilogue with the next tile's MMAs.
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
@@ -52,7 +53,9 @@ struct Params {
     int KH, KW, stride, pad_h, pad_w, act;
     int tiles_w, tiles_h;
     int per_image_w;               // weights are (N, Cout, KH*KW*Cin): the CTA's image selects the matrix
-    int debug;                     // development only (MFB_CONV_DEBUG): 1 = skip the global stores, 2 = skip the TMEM loads, 4 = producer/MMA idle
+    int debug;                     // development only (MFB_CONV_DEBUG, tools/conv_experiment.py): bit 0 = skip the transposed global
+                                   // stores, bit 1 = skip the TMEM loads (that experiment showed neither was the limiter of the
+                                   // narrow-input 1x1 layers: 32-byte TMA rows were; see encoder_fast._fold_pixels)
     __nv_bfloat16* y;              // nullptr in head mode
     const __nv_bfloat16* res;      // residual added before the activation, or nullptr
     const float* scale;
