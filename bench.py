@@ -456,13 +456,44 @@ def block_cfg4_e2e(dev, steps, net, host, calib):
             h_cost.copy_(sim.last_cost, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return h_cost.view(scenes, per_scene).argmin(dim=1)
-    ms = timed_ms(call, max(steps // 2, 5))
+    ms_serial = timed_ms(call, max(steps // 2, 5))
     ms_nf = timed_ms(lambda: call(False), max(steps // 2, 5))
     sim.return_forces = True
+
+    # steady state of a planner loop: the NEXT frame's images and controls are uploaded on a copy stream while the current
+    # frame is encoded and rolled out; every step still uploads one frame and reads one set of costs back
+    copy_stream = torch.cuda.Stream(device=dev)
+    img = [host[0].to(dev), host[0].to(dev)]
+    cdev = [ctrl.to(dev), ctrl.to(dev)]
+    ev_up = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+    for e in ev_up + ev_done:
+        e.record()
+    st = {"i": 0}
+
+    def piped():
+        cur = st["i"] & 1
+        main = torch.cuda.current_stream()
+        main.wait_event(ev_up[cur])
+        with torch.no_grad():
+            out = net(img[cur], *calib)
+            sim(out["terrain"].squeeze(1), cdev[cur], friction=out["friction"].squeeze(1))
+            h_cost.copy_(sim.last_cost, non_blocking=True)
+        ev_done[cur].record(main)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_done[1 - cur])
+            img[1 - cur].copy_(host[0], non_blocking=True)
+            cdev[1 - cur].copy_(ctrl, non_blocking=True)
+            ev_up[1 - cur].record(copy_stream)
+        main.synchronize()                                   # the planner reads this frame's costs before it goes on
+        st["i"] += 1
+        return h_cost.view(scenes, per_scene).argmin(dim=1)
+    ms = timed_ms(piped, max(steps // 2, 5))
     return {"workload": "images (host) -> LiftSplatShoot (eval) -> terrain/friction (16 x 256x256) -> DPhysics rollout, 16 scenes x "
                         "256 trajectories x T=400 (one map per scene), all reference outputs materialised + fused cost -> costs on host",
-            "ms": ms, "scenes_per_s": scenes / (ms * 1e-3), "trajectory_steps_per_s": n * T_STEPS / (ms * 1e-3),
-            "ms_without_force_tensors": ms_nf, "h2d_bytes": host[0].numel() * 4 + ctrl.numel() * 4, "d2h_bytes": n * 4, **parts}
+            "ms": ms, "ms_upload_then_compute_one_stream": ms_serial, "scenes_per_s": scenes / (ms * 1e-3),
+            "trajectory_steps_per_s": n * T_STEPS / (ms * 1e-3), "ms_without_force_tensors_one_stream": ms_nf,
+            "pipelining": "the next frame's upload (images + controls) overlaps the current frame's kernels; costs are read back every step", "h2d_bytes": host[0].numel() * 4 + ctrl.numel() * 4, "d2h_bytes": n * 4, **parts}
 
 
 def main():
