@@ -335,7 +335,8 @@ def block_small_batch(dev, steps):
         physics_loss(st, gt, ts, ts).backward()
     lat2 = wall_ms(train, max(steps, 10))
     out["training_B16_T500_distinct_32x32_odeint_fwd_bwd"] = {**lat2, "trajectory_steps_per_s": bsz * T / (lat2["median_ms"] * 1e-3)}
-    out["note"] = "one warp per trajectory: 64 trajectories occupy 16 of 148 SMs; these are latencies, not throughputs"
+    out["note"] = ("forward = the small-batch kernel K1w (one CTA per trajectory, two contact points per thread; the library picks "
+                   "it below 512 / 1024 trajectories, rollout_fwd.cu); these are latencies, not throughputs")
     return out
 
 

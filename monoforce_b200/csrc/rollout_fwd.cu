@@ -1,7 +1,9 @@
 // Instantiations + PPL dispatcher of the forward rollout kernel (K1) for one
 // (scalar type, integrator variant) pair: -DMFB_INST_T=... -DMFB_INST_VARIANT=...
 #include "launch.h"
+#include <cstdlib>
 #include "rollout_fwd.cuh"
+#include "rollout_fwd_wide.cuh"
 
 #ifndef MFB_INST_T
 #error "compile with -DMFB_INST_T=float|double -DMFB_INST_VARIANT=0|1"
@@ -42,10 +44,41 @@ static LaunchError launch_ppl(const RolloutArgs<T>& a, cudaStream_t st) {
     return go(rollout_fwd_kernel<T, PPL, VARIANT, false, false>);
 }
 
+// Small batches: one CTA per trajectory, two contact points per thread (K1w).  Below ~2 warps per scheduler the one-warp-per-
+// trajectory kernel is bound by single-warp latency; K1w shortens the instruction stream each warp walks per step.  Measured
+// crossover on B200 (tools/fwd_crossover.py, T = 500, marv): step loop B ~ 512 (1.05 vs 1.09 ms; 0.69 vs 1.08 ms at B = 64),
+// odeint variant B ~ 2048 (0.65 vs 1.26 ms at B = 64).  MFB_FWD_WIDE_MAX_B overrides the batch-size threshold (0 disables the
+// wide kernel; tests force either path).
+static int wide_max_b(int variant) {
+    const char* e = getenv("MFB_FWD_WIDE_MAX_B");
+    return e ? atoi(e) : (variant == kOdeintEuler ? 1024 : 512);
+}
+
+template <typename T, int VARIANT>
+static LaunchError launch_wide(const RolloutArgs<T>& a, cudaStream_t st) {
+    const dim3 grid(a.B), block(((a.N + 32 * kWidePts - 1) / (32 * kWidePts)) * 32);
+    const bool forces = a.Fs != nullptr, cost = a.cost != nullptr;
+    auto go = [&](auto kern) -> LaunchError {
+        kern<<<grid, block, 0, st>>>(a);
+        count_launch();
+        return {nullptr};
+    };
+    if (VARIANT == kOdeintEuler) {
+        if (cost) return {"cost output is defined for the step-loop variant only"};
+        if (forces) return go(rollout_fwd_wide_kernel<T, VARIANT, true, false>);
+        return go(rollout_fwd_wide_kernel<T, VARIANT, false, false>);
+    }
+    if (forces && cost) return go(rollout_fwd_wide_kernel<T, VARIANT, true, true>);
+    if (forces) return go(rollout_fwd_wide_kernel<T, VARIANT, true, false>);
+    if (cost) return go(rollout_fwd_wide_kernel<T, VARIANT, false, true>);
+    return go(rollout_fwd_wide_kernel<T, VARIANT, false, false>);
+}
+
 template <>
 LaunchError launch_rollout_fwd<MFB_INST_T, MFB_INST_VARIANT>(const RolloutArgs<MFB_INST_T>& a, cudaStream_t st) {
     using T = MFB_INST_T;
     constexpr int V = MFB_INST_VARIANT;
+    if (!a.joint_angles && a.B <= wide_max_b(V)) return launch_wide<T, V>(a, st);
     const int ppl = (a.N + 31) / 32;
     switch (ppl) {
         case 1: return launch_ppl<T, 1, V>(a, st);

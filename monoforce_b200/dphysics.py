@@ -241,6 +241,17 @@ class DPhysics(torch.nn.Module):
         gradients are required, which lets the backward run the single-sweep adjoint kernel.
     """
 
+    # attributes rewritten on every call with plain tensors / flags (the reference does the same, :561-581): they skip
+    # nn.Module.__setattr__'s Parameter / buffer / sub-module bookkeeping, ~10 assignments per call on the planner's latency path
+    _PER_CALL = frozenset({'controls', 'joint_angles', 'ts', 'z_grid', 'friction', '_z_arg', '_mu_arg', '_x0z', 'last_cost',
+                           '_moving_joints'})
+
+    def __setattr__(self, name, value):
+        if name in DPhysics._PER_CALL:
+            self.__dict__[name] = value
+        else:
+            super().__setattr__(name, value)
+
     def __init__(self, dphys_cfg=None, device='cpu'):
         super().__init__()
         self.dphys_cfg = DPhysConfig() if dphys_cfg is None else dphys_cfg
@@ -347,6 +358,22 @@ class DPhysics(torch.nn.Module):
         self.last_cost = cost if meta.want_cost else None
         return Xs, Xds, Rs, Oms, Fs, Ff
 
+    def _zero_scalar(self, dtype):
+        key = ('zero', str(self.device), dtype)
+        if key not in self._const_cache:
+            self._const_cache[key] = torch.zeros((), device=self.device, dtype=dtype)
+        return self._const_cache[key]
+
+    def _default_friction(self):
+        """`dphys_cfg.friction` as a (1,H,W) tensor on self.device, uploaded once per (tensor, version, device) instead of once
+        per call (a pageable host->device copy blocks the host behind the previous call's kernel)."""
+        f = self.dphys_cfg.friction
+        key = (id(f), f._version, str(self.device))
+        if self.__dict__.get('_fric_key') != key:
+            self.__dict__['_fric_dev'] = f.to(self.device).unsqueeze(0)
+            self.__dict__['_fric_key'] = key
+        return self.__dict__['_fric_dev']
+
     def _shared_view(self, grid, B):
         """(1,H,W) view when all B trajectories read one map: a broadcast / `expand`ed input, or - what the reference's
         callers pass (monoforce_node.py:156, diff_physics.ipynb cell 3) - B materialised `repeat`s of one map.  Repeats
@@ -418,15 +445,16 @@ class DPhysics(torch.nn.Module):
             # the reference articulates the body only for marv with non-zero angles (:340; one host sync per CALL
             # here instead of one per step there)
             self._moving_joints = cfg.robot == 'marv' and bool(torch.any(joint_angles != 0))
+        # (zero angles are never read by the kernels: a stride-0 view keeps the attribute's shape without a fill per call)
         self.joint_angles = joint_angles if joint_angles is not None else \
-            torch.zeros((B, N_ts, 4), device=self.device, dtype=dtype)
+            self._zero_scalar(dtype).expand(B, N_ts, 4)
         self.ts = self.ts[:N_ts]                                                # :581
         if self.ts.shape[0] != N_ts:
             raise AssertionError(f'time grid has {self.ts.shape[0]} samples, need {N_ts}')
 
         cdev = self._compute_device()
         if friction is None:                                                    # :562 (no B copies: stride-0 view)
-            friction = cfg.friction.to(self.device).unsqueeze(0)
+            friction = self._default_friction()
         self.z_grid = z_grid.to(self.device)                                    # :563-564
         self.friction = friction.to(self.device)
         self._z_arg = self._shared_view(self.z_grid, batch_size).to(cdev)

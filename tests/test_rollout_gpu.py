@@ -21,6 +21,15 @@ DEV = "cuda"
 ADJOINT_TAPE = True      # flipped by the `adjoint_kernel` fixture: single-sweep (tape) vs three-pass adjoint
 
 
+@pytest.fixture(params=["warp", "wide"], autouse=True)
+def forward_kernel(request, monkeypatch):
+    """Every test of this module runs once per forward kernel: K1 (one warp per trajectory, the large-batch kernel) and K1w
+    (one CTA per trajectory, one thread per contact point, the small-batch kernel).  The library reads the batch-size threshold
+    from MFB_FWD_WIDE_MAX_B at each launch (moving flippers always take K1)."""
+    monkeypatch.setenv("MFB_FWD_WIDE_MAX_B", "0" if request.param == "warp" else str(1 << 30))
+    yield request.param
+
+
 @pytest.fixture(params=["sweep", "three_pass"])
 def adjoint_kernel(request):
     """Runs an adjoint test once per backward kernel: K2s (single sweep, reads the forward's contact_sum tape)
@@ -491,6 +500,36 @@ def test_forward_envelope_on_bench_inputs(case):
     for k, v in r.items():
         assert v["kernel_median"] <= 3 * v["ref32_median"] + 1e-6, (k, v)
         assert v["kernel_max"] <= 3 * v["ref32_max"] + 1e-5, (k, v)
+
+
+@pytest.mark.parametrize("variant", ["step", "odeint"])
+def test_forward_kernel_dispatch_by_batch_size(variant, monkeypatch, forward_kernel):
+    """Without MFB_FWD_WIDE_MAX_B the library picks K1w for planner-size batches and K1 for large ones (rollout_fwd.cu:
+    wide_max_b): the default's output is bit-identical to the forced kernel it should have picked, and the two kernels
+    agree to fp32 round-off (they associate the per-step sums differently)."""
+    if forward_kernel != "warp":
+        pytest.skip("one run is enough: the test sets the threshold itself")
+    T = 60
+    sim, cfg = _module("marv", 0.1, T, variant)
+    z = hill_map(cfg).to(DEV)[None]
+
+    def run(B, thr):
+        if thr is None:
+            monkeypatch.delenv("MFB_FWD_WIDE_MAX_B", raising=False)
+        else:
+            monkeypatch.setenv("MFB_FWD_WIDE_MAX_B", thr)
+        ctrl = torch.stack([torch.rand(B, 1, generator=torch.Generator().manual_seed(B)) * 2 - 1,
+                            torch.rand(B, 1, generator=torch.Generator().manual_seed(B + 1)) * 2 - 1], -1).repeat(1, T, 1).to(DEV)
+        with torch.no_grad():
+            st, fo = sim(z, ctrl)
+        return [t.clone() for t in st + fo]
+    for B, picked in ((64, str(1 << 30)), (2048, "0")):
+        default, wide, warp = run(B, None), run(B, str(1 << 30)), run(B, "0")
+        forced = wide if picked != "0" else warp
+        assert all(torch.equal(a, b) for a, b in zip(default, forced)), (B, picked)
+        assert not all(torch.equal(a, b) for a, b in zip(wide, warp))            # they are different kernels
+        for a, b, tol in zip(wide[:4], warp[:4], (1e-4, 5e-3, 1e-4, 5e-3)):      # poses 1e-4; velocities jump at contact changes
+            assert rel_err(a, b) < tol
 
 
 def test_per_trajectory_maps_and_off_map_clamp():
