@@ -17,7 +17,7 @@ static LaunchError launch_ppl(const RolloutArgs<T>& a, cudaStream_t st) {
     const bool forces = a.Fs != nullptr, cost = a.cost != nullptr;
     if (forces && ((((uintptr_t)a.Fs) | ((uintptr_t)a.Ff)) & 15))
         return {"F_springs / F_frictions must be 16-byte aligned (rows leave the SM as TMA bulk stores)"};
-    const size_t smem = forces ? RowStage<T>::smem_bytes(a.N, kFwdWarps) : 0;
+    const size_t smem = forces ? RowStage<T>::smem_bytes(a.N, kFwdWarps, VARIANT) : 0;
     auto go = [&](auto kern) -> LaunchError {
         // static (point table) + dynamic (row images) can exceed the 48 KB default: always opt in
         if (smem > 0 &&
