@@ -34,7 +34,7 @@ def _nvcc() -> str:
 def _units():
     units = [("c_api", "c_api.cu", []), ("lift_splat", "lift_splat.cu", []),
              ("conv_tcgen05", "conv_tcgen05.cu", []), ("physics_loss", "physics_loss.cu", []),
-             ("encoder_ops", "encoder_ops.cu", [])]
+             ("encoder_ops", "encoder_ops.cu", []), ("dwconv_tma", "dwconv_tma.cu", [])]
     for kern in ("rollout_fwd", "rollout_bwd"):
         for tname in ("float", "double"):
             for variant in (0, 1):

@@ -5,13 +5,13 @@
 //                     and the x2 nn.Upsample in front of every BEV head                  lss.py:117-139
 //   stem_conv         EfficientNet-B0 stem: 3x3/2 conv (TF "same" padding) + BN + swish  lss.py:78 (efficientnet_pytorch 0.7.1)
 //   dwconv            MBConv depthwise k x k conv + BN + swish, with the squeeze-excite
-//                     global average pool accumulated on the fly                        lss.py:83-90 (MBConvBlock.forward)
+//                     global average pool accumulated on the fly (kernel: dwconv_tma.cu)  lss.py:83-90 (MBConvBlock.forward)
 //   se_fold           squeeze-excite MLP (reduce -> swish -> expand -> sigmoid) per image, folded into that image's copy
 //                     of the 1x1 projection matrix:  W_n[co,c] = W[co,c] * s_n[c]   (x * s) @ W^T == x @ W_n^T
 //   cast              fp32 -> bf16 (the lift-splat BEV grid is accumulated with fp32 atomics)
 //
-// All of them are HBM-bound: 16-byte vector loads / stores along the channel axis, fp32 arithmetic, one thread per
-// (pixel, 8-channel group).  Eval-mode BatchNorm is pre-folded by the host: weights carry the scale, `shift` the rest.
+// Apart from the depthwise convolution (fp32-FMA-bound, its own file) they are HBM-bound: 16-byte vector loads / stores along
+// the channel axis, fp32 arithmetic, one thread per (pixel, 8-channel group).  Eval-mode BatchNorm is pre-folded by the host: weights carry the scale, `shift` the rest.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,6 +23,10 @@
 namespace mfb {
 void count_launch();
 int fail_status(int code, const std::string& msg);
+namespace enc {
+int launch_dwconv_tma(const void* x, const float* w, const float* shift, void* y, float* pool, int N, int H, int W, int C, int Ho,
+                      int Wo, int K, int stride, int pad_h, int pad_w, cudaStream_t st);
+}
 
 namespace enc {
 
@@ -40,15 +44,6 @@ __device__ __forceinline__ Bf8 pack8(const float* f) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) b.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
     return b;
-}
-// acc[0..7] += t[0..7] * w[0..7] as four packed fma.rn.f32x2 (FFMA2: two FMAs per issue slot on sm_100a; the depthwise kernels
-// are issue-bound, and the bf16 unpack already leaves channel pairs in adjacent registers)
-__device__ __forceinline__ void fma8(float* acc, const float* t, const float* w) {
-#pragma unroll
-    for (int k = 0; k < 8; k += 2) {
-        const float2 r = __ffma2_rn(make_float2(t[k], t[k + 1]), make_float2(w[k], w[k + 1]), make_float2(acc[k], acc[k + 1]));
-        acc[k] = r.x; acc[k + 1] = r.y;
-    }
 }
 __device__ __forceinline__ Bf8 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const Bf8*>(p); }
 // x sigmoid(x) = x/2 (1 + tanh(x/2)): one SFU op + 2 FMA-class instructions (tanh.approx: 2^-11 relative, below bf16 rounding)
@@ -108,320 +103,115 @@ upsample_concat_kernel(const __nv_bfloat16* __restrict__ skip, const __nv_bfloat
 
 // ---------------------------------------------------------------------------------------------------------------
 // stem: img (N,3,H,W) fp32 NCHW -> y (N,Ho,Wo,32) bf16 NHWC; 3x3 stride 2, low-side padding (ph, pw); weights (3,3,3,32)
-// fp32 [dy][dx][ci][co] with the BN scale folded; y = swish(conv + shift).  The 864 weights + 32 shifts travel BY VALUE as
-// a kernel parameter: they sit in the constant bank and feed the FMAs as immediate operands (no load instruction per
-// FMA; from shared memory the kernel was LDS-bound: 216 LDS.128 per 864 FMAs, 0.45 ms at 64 x 512 x 512).
+// fp32 [dy][dx][ci][co] with the BN scale folded; y = swish(conv + shift).
+// As a GEMM the layer is (pixels) x 27 x 32.  On the fp32 pipe it needs 864 FMAs per pixel and was FMA-bound (0.33 ms at
+// 64 x 512 x 512, where its 0.47 GB of traffic take 0.08 ms), so the contraction runs on the tensor cores: a warp gathers the
+// im2col rows of 16 consecutive output pixels straight into mma.sync.m16n8k16 bf16 A fragments (K padded 27 -> 32, image and
+// weights rounded to bf16 like every other layer of the trunk, fp32 accumulate), 8 MMAs per 16 pixels.  mma.sync rather than
+// tcgen05 on purpose: K = 27 and N = 32 make the tensor op ~2 % of the kernel; the work is the gather and the 64-byte rows.
+// The weights travel BY VALUE as a kernel parameter (2 KB bf16 + shifts): every lane reads its B fragments from the constant
+// bank once.  Output rows of the 16 pixels are contiguous (1 KB): they leave through a per-warp staging tile as 16-byte stores.
 // ---------------------------------------------------------------------------------------------------------------
-struct StemWeights { float w[27 * 32]; float shift[32]; };
+struct StemWeights { uint16_t w[32][32]; float shift[32]; };          // w[k][co] bf16 bits, k = (dy * 3 + dx) * 3 + ci, rows 27..31 zero
+constexpr int kStemWarps = 8;
 
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kStemWarps * 32)
 stem_conv_kernel(const float* __restrict__ img, const __grid_constant__ StemWeights sw, __nv_bfloat16* __restrict__ y, int N,
                  int H, int W, int Ho, int Wo, int ph, int pw) {
-    const unsigned total = (unsigned)N * Ho * Wo;            // host guarantees < 2^31 output pixels
-    for (unsigned pix = blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += gridDim.x * blockDim.x) {
-        const int wo = (int)(pix % (unsigned)Wo);
-        const unsigned nh = pix / (unsigned)Wo;
-        const int ho = (int)(nh % (unsigned)Ho);
-        const int n = (int)(nh / (unsigned)Ho);
-        float acc[32];
+    __shared__ __align__(16) uint32_t stage[kStemWarps][16][17];       // 16 pixels x 32 bf16 (16 words), +1 word: conflict-free
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const unsigned total = (unsigned)N * Ho * Wo;                       // host guarantees < 2^31 output pixels
+    const unsigned tiles = (total + 15) / 16;
+    const long long HW = (long long)H * W;
+
+    // this lane's 8 im2col columns: k = 2t, 2t+1, 2t+8, 2t+9 (+16 for the second k-step); offset / tap position of each
+    int koff[8], kdy[8], kdx[8];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = sw.shift[c];
-        const float* base = img + (long long)n * 3 * H * W;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            const int hi = 2 * ho + dy - ph;
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-                const int wi = 2 * wo + dx - pw;
-                const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
-#pragma unroll
-                for (int ci = 0; ci < 3; ++ci) {
-                    const float v = ok ? __ldg(base + ((long long)ci * H + hi) * W + wi) : 0.f;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) acc[c] = fmaf(v, sw.w[((dy * 3 + dx) * 3 + ci) * 32 + c], acc[c]);
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c] = silu(acc[c]);
-        Bf8* dst = reinterpret_cast<Bf8*>(y + (long long)pix * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = pack8(acc + 8 * q);
+    for (int j = 0; j < 8; ++j) {
+        const int k = 2 * t + (j & 1) + ((j >> 1) & 1) * 8 + (j >> 2) * 16;
+        const int tap = k / 3, ci = k - tap * 3, dy = tap / 3, dx = tap - dy * 3;
+        const bool real = k < 27;
+        kdy[j] = real ? dy : 0; kdx[j] = real ? dx : 0;                  // padded columns read a valid pixel; their weights are 0
+        koff[j] = real ? (int)(ci * HW) + dy * W + dx : 0;
     }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// depthwise k x k conv + shift + swish; pool[n,c] += sum over the pixels of the output (fp32)
-// x (N,H,W,C), y (N,Ho,Wo,C) bf16; w (K*K, C) fp32 (BN scale folded).
-// Work item = a strip of kDwStrip consecutive output pixels of one row x one 8-channel group: the input row segment of a
-// tap row is loaded once and slides over the strip (k + (S-1)*stride loads per tap row instead of k*S), weights once per
-// tap.  A CTA owns all C/8 channel groups of P = blockDim / G strips at a time and walks `rows` strips per thread (up to 8;
-// fewer on the small feature maps, so that the grid still fills the GPU a few times over), so its squeeze-excite partial
-// sums leave as ONE atomicAdd per channel for up to P * rows * kDwStrip pixels.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kDwStrip = 4, kDwMaxRows = 8;
-
-template <int K, int STRIDE>
-__global__ void __launch_bounds__(256, 2)
-dwconv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
-              __nv_bfloat16* __restrict__ y, float* __restrict__ pool, int H, int W, int C, int Ho, int Wo, int ph, int pw,
-              int rows) {
-    extern __shared__ float pool_s[];                      // C partial sums of this CTA
-    constexpr int S = kDwStrip;
-    constexpr int IN = K + (S - 1) * STRIDE;               // input pixels a strip needs per tap row
-    const int n = blockIdx.y;
-    const int G = C >> 3;
-    const int P = blockDim.x / G;                          // strips in flight per CTA (host guarantees >= 1)
-    const int g = threadIdx.x % G, slot = threadIdx.x / G;
-    const int c = g << 3;
-    const int strips_w = (Wo + S - 1) / S;
-    const int n_strips = Ho * strips_w;
-    if (pool) {
-        for (int i = threadIdx.x; i < C; i += blockDim.x) pool_s[i] = 0.f;
-        __syncthreads();
+    // B fragments: b[ks][nt] = {B[16 ks + 2t][8 nt + g], B[.. + 1][..]}, {B[16 ks + 2t + 8][..], B[.. + 9][..]}
+    uint32_t bfrag[2][4][2];
+    float shv[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const int k0 = 16 * ks + 2 * t, n = 8 * nt + g;
+            bfrag[ks][nt][0] = (uint32_t)sw.w[k0][n] | ((uint32_t)sw.w[k0 + 1][n] << 16);
+            bfrag[ks][nt][1] = (uint32_t)sw.w[k0 + 8][n] | ((uint32_t)sw.w[k0 + 9][n] << 16);
+        }
+        shv[nt][0] = sw.shift[8 * nt + 2 * t];
+        shv[nt][1] = sw.shift[8 * nt + 2 * t + 1];
     }
-    float sh[8];
-    {
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + c)), s1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
-        sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
-    }
-    float psum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const __nv_bfloat16* xin = x + (long long)n * H * W * C + c;
-    __nv_bfloat16* yout = y + (long long)n * Ho * Wo * C + c;
-    if (slot < P) {
-        for (int r = 0; r < rows; ++r) {
-            const int sid = (blockIdx.x * rows + r) * P + slot;
-            if (sid >= n_strips) break;
-            const int ho = sid / strips_w, wo0 = (sid - ho * strips_w) * S;
-            float acc[S][8];
-#pragma unroll
-            for (int j = 0; j < S; ++j)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[j][k] = sh[k];
-            const int wi0 = wo0 * STRIDE - pw;
-#pragma unroll
-            for (int dy = 0; dy < K; ++dy) {
-                const int hi = ho * STRIDE + dy - ph;
-                if (hi < 0 || hi >= H) continue;
-                const __nv_bfloat16* row = xin + (long long)hi * W * C;
-                // input-stationary: the row segment is loaded once (packed), every pixel is unpacked ONCE and feeds all the
-                // (output j, tap dx) pairs with j*STRIDE + dx == i; the K weights of this tap row sit in registers
-                Bf8 v[IN];
-                const __nv_bfloat16* p0 = row + (long long)wi0 * C;       // may point before the row: only dereferenced in range
-                if (wi0 >= 0 && wi0 + IN <= W) {                          // interior strip: no per-pixel bounds tests
-#pragma unroll
-                    for (int i = 0; i < IN; ++i) v[i] = ld8(p0 + i * C);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < IN; ++i) {
-                        const int wi = wi0 + i;
-                        uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                        if (wi >= 0 && wi < W) z = *reinterpret_cast<const uint4*>(p0 + i * C);
-                        *reinterpret_cast<uint4*>(&v[i]) = z;
-                    }
-                }
-                float wk[K][8];
-#pragma unroll
-                for (int dx = 0; dx < K; ++dx) {
-                    const float* wr = w + (dy * K + dx) * C + c;
-                    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wr)), w1 = __ldg(reinterpret_cast<const float4*>(wr + 4));
-                    wk[dx][0] = w0.x; wk[dx][1] = w0.y; wk[dx][2] = w0.z; wk[dx][3] = w0.w;
-                    wk[dx][4] = w1.x; wk[dx][5] = w1.y; wk[dx][6] = w1.z; wk[dx][7] = w1.w;
-                }
-#pragma unroll
-                for (int i = 0; i < IN; ++i) {
-                    float t[8];
-                    unpack8(v[i], t);
-#pragma unroll
-                    for (int j = 0; j < S; ++j) {
-                        const int dx = i - j * STRIDE;
-                        if (dx >= 0 && dx < K) {
-                            fma8(acc[j], t, wk[dx]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < S; ++j) {
-                if (wo0 + j < Wo) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[j][k] = silu(acc[j][k]);
-                    *reinterpret_cast<Bf8*>(yout + ((long long)ho * Wo + wo0 + j) * C) = pack8(acc[j]);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) psum[k] += acc[j][k];      // squeeze-excite pool in fp32 (before the bf16 rounding)
-                }
-            }
-        }
-    }
-    if (pool) {
-        if (slot < P) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) atomicAdd(pool_s + c + k, psum[k]);      // P-way contention at most (P = 256 / G)
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < C; i += blockDim.x) {
-            const float v = pool_s[i];
-            if (v != 0.f) atomicAdd(pool + (long long)n * C + i, v);
-        }
-    }
-}
 
-// ---------------------------------------------------------------------------------------------------------------
-// Stride-1 depthwise conv through a shared-memory tile (the layers where the strip kernel above was latency-bound: every
-// thread waited for its own tap-row loads before its FMAs).  A CTA owns TH x TW output pixels x 32 channels of one image:
-// the (TH + K - 1) x (TW + K - 1) input patch is brought in with cp.async (16 bytes per request, zero-filled outside the
-// image = the conv's padding), then each thread computes one 4-pixel strip x 8 channels from shared memory.  Several CTAs
-// per SM overlap one CTA's loads with another's FMAs.  Pixel pitch in shared memory = 64 + 16 bytes: conflict-free LDS.128.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kDwSlab = 32;                      // channels per CTA
-constexpr int kDwPitch = kDwSlab * 2 + 16;       // bytes per staged pixel
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, bool valid) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 16 : 0;               // src-size 0: the 16 bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gmem_src), "r"(sz) : "memory");
-}
-
-constexpr int kDwChunk = 16;                     // spatial tiles of one (image, channel slab) a CTA works through before it flushes its pool sums
-
-template <int K>
-__global__ void __launch_bounds__(256, 2)
-dwconv_tile_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ shift,
-                   __nv_bfloat16* __restrict__ y, float* __restrict__ pool, int N, int H, int W, int C, int ph, int pw, int TW,
-                   int TH) {
-    // Persistent and double-buffered: a CTA walks work units = (image, 32-channel slab, chunk of up to 16 spatial tiles); the
-    // cp.async requests of tile i+1 are in flight while tile i is computed, and the squeeze-excite partial sums stay in
-    // registers for a whole unit (one shuffle-reduce + one atomic per channel per unit instead of per tile).
-    extern __shared__ __align__(16) unsigned char dw_smem[];
-    constexpr int S = kDwStrip, IN = K + S - 1;
-    float* pool_s = reinterpret_cast<float*>(dw_smem);                 // [32]
-    const int TWI = TW + K - 1, THI = TH + K - 1;
-    const int tile_bytes = THI * TWI * kDwPitch;
-    unsigned char* const buf0 = dw_smem + 128;
-    const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
-    const int sp_tiles = tiles_w * tiles_h;
-    const int chunks = (sp_tiles + kDwChunk - 1) / kDwChunk;
-    const int slabs = (C + kDwSlab - 1) / kDwSlab;
-    const int units = N * slabs * chunks;
-
-    // cp.async staging of spatial tile q of (image n, slab): thread i handles patch entries i, i + 256, ... (entry = pixel * 4 + group)
-    const int e_pix0 = threadIdx.x >> 2, e_g = threadIdx.x & 3;
-    const int e_iy0 = e_pix0 / TWI, e_ix0 = e_pix0 - e_iy0 * TWI;     // one division per kernel, then incremental
-    const int step_iy = 64 / TWI, step_ix = 64 - step_iy * TWI;
-    auto stage = [&](int n, int slab, int q, unsigned char* tile) {
-        const int h0 = (q / tiles_w) * TH, w0 = (q % tiles_w) * TW, c0 = slab * kDwSlab;
-        const bool gok = e_g < min(4, (C - c0) >> 3);
-        const __nv_bfloat16* xin = x + (long long)n * H * W * C + c0 + e_g * 8;
-        int ix = e_ix0, iy = e_iy0;
-        for (int pxy = e_pix0; pxy < THI * TWI; pxy += 64) {
-            const int hi = h0 + iy - ph, wi = w0 + ix - pw;
-            const bool ok = gok && hi >= 0 && hi < H && wi >= 0 && wi < W;
-            cp_async16(tile + pxy * kDwPitch + e_g * 16, ok ? xin + ((long long)hi * W + wi) * C : xin, ok);
-            ix += step_ix; iy += step_iy;
-            if (ix >= TWI) { ix -= TWI; ++iy; }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-
-    // thread -> (strip, channel group): 4 groups x (TW/4) strips x TH rows = 256 threads
-    const int g = threadIdx.x & 3;
-    const int sidx = threadIdx.x >> 2;
-    const int sw = sidx % (TW / S), sh = sidx / (TW / S);
-
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int n = u / (slabs * chunks), r = u - n * slabs * chunks;
-        const int slab = r / chunks, q0 = (r - slab * chunks) * kDwChunk;
-        const int q1 = min(q0 + kDwChunk, sp_tiles);
-        const int c0 = slab * kDwSlab;
-        const int gmax = min(4, (C - c0) >> 3);
-        const int c = c0 + g * 8;
-        const bool live = g < gmax && sh < TH;
-        float sh8[8], psum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (live) {
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + c)), s1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
-            sh8[0] = s0.x; sh8[1] = s0.y; sh8[2] = s0.z; sh8[3] = s0.w; sh8[4] = s1.x; sh8[5] = s1.y; sh8[6] = s1.z; sh8[7] = s1.w;
-        }
-        __syncthreads();                                                    // the previous unit is done with both buffers and pool_s
-        if (threadIdx.x < 32) pool_s[threadIdx.x] = 0.f;
-        stage(n, slab, q0, buf0);
-        for (int q = q0, it = 0; q < q1; ++q, ++it) {
-            unsigned char* const tile = buf0 + (it & 1) * tile_bytes;
-            if (q + 1 < q1) {
-                stage(n, slab, q + 1, buf0 + ((it + 1) & 1) * tile_bytes);      // prefetch the next tile into the other buffer
-                asm volatile("cp.async.wait_group 1;" ::: "memory");            // ... and wait for the current one only
+    for (unsigned tile = blockIdx.x * kStemWarps + warp; tile < tiles; tile += gridDim.x * kStemWarps) {
+        // rows g and g + 8 of the tile = output pixels p0, p1
+        float av[2][8];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            unsigned pix = tile * 16 + g + 8 * r;
+            const bool live = pix < total;
+            pix = live ? pix : total - 1;
+            const int wo = (int)(pix % (unsigned)Wo);
+            const unsigned nh = pix / (unsigned)Wo;
+            const int ho = (int)(nh % (unsigned)Ho), n = (int)(nh / (unsigned)Ho);
+            const int iy0 = 2 * ho - ph, ix0 = 2 * wo - pw;
+            const float* base = img + (long long)n * 3 * HW + (long long)iy0 * W + ix0;
+            if (iy0 >= 0 && iy0 + 2 < H && ix0 >= 0 && ix0 + 2 < W) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) av[r][j] = __ldg(base + koff[j]);
             } else {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-            }
-            __syncthreads();
-            if (live) {
-                const int h0 = (q / tiles_w) * TH, w0 = (q % tiles_w) * TW;
-                float acc[S][8];
 #pragma unroll
-                for (int j = 0; j < S; ++j)
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[j][k] = sh8[k];
-#pragma unroll
-                for (int dy = 0; dy < K; ++dy) {
-                    const unsigned char* row = tile + ((sh + dy) * TWI + sw * S) * kDwPitch + g * 16;
-                    float wk[K][8];
-#pragma unroll
-                    for (int dx = 0; dx < K; ++dx) {
-                        const float* wr = w + (dy * K + dx) * C + c;
-                        const float4 w0v = __ldg(reinterpret_cast<const float4*>(wr)), w1v = __ldg(reinterpret_cast<const float4*>(wr + 4));
-                        wk[dx][0] = w0v.x; wk[dx][1] = w0v.y; wk[dx][2] = w0v.z; wk[dx][3] = w0v.w;
-                        wk[dx][4] = w1v.x; wk[dx][5] = w1v.y; wk[dx][6] = w1v.z; wk[dx][7] = w1v.w;
-                    }
-#pragma unroll
-                    for (int i = 0; i < IN; ++i) {
-                        float tv[8];
-                        unpack8(*reinterpret_cast<const Bf8*>(row + i * kDwPitch), tv);
-#pragma unroll
-                        for (int j = 0; j < S; ++j) {
-                            const int dx = i - j;
-                            if (dx >= 0 && dx < K) {
-fma8(acc[j], tv, wk[dx]);
-                            }
-                        }
-                    }
-                }
-                const int ho = h0 + sh;
-                if (ho < H) {
-                    __nv_bfloat16* yout = y + (((long long)n * H + ho) * W) * C + c;
-#pragma unroll
-                    for (int j = 0; j < S; ++j) {
-                        const int wo = w0 + sw * S + j;
-                        if (wo < W) {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) acc[j][k] = silu(acc[j][k]);
-                            *reinterpret_cast<Bf8*>(yout + (long long)wo * C) = pack8(acc[j]);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) psum[k] += acc[j][k];
-                        }
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const bool ok = (unsigned)(iy0 + kdy[j]) < (unsigned)H && (unsigned)(ix0 + kdx[j]) < (unsigned)W;
+                    av[r][j] = ok ? __ldg(base + koff[j]) : 0.f;
                 }
             }
-            __syncthreads();              // everyone is done with this tile's buffer (it is the prefetch target of the next iteration)
         }
-        if (pool) {
-            // lanes l, l+4, l+8 ... of a warp hold the same channel group: fold them with xor-shuffles, then 8 shared atomics per group
+        float d[4][4];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                float v = psum[k];
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                psum[k] = v;
-            }
-            if ((threadIdx.x & 31) < 4 && g < gmax) {
+        for (int nt = 0; nt < 4; ++nt) { d[nt][0] = d[nt][2] = shv[nt][0]; d[nt][1] = d[nt][3] = shv[nt][1]; }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) atomicAdd(pool_s + g * 8 + k, psum[k]);
-            }
-            __syncthreads();
-            if (threadIdx.x < 32 && c0 + (int)threadIdx.x < C) {
-                const float v = pool_s[threadIdx.x];
-                if (v != 0.f) atomicAdd(pool + (long long)n * C + c0 + threadIdx.x, v);
+        for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t a0 = pack_bf16x2(av[0][4 * ks + 0], av[0][4 * ks + 1]), a1 = pack_bf16x2(av[1][4 * ks + 0], av[1][4 * ks + 1]);
+            const uint32_t a2 = pack_bf16x2(av[0][4 * ks + 2], av[0][4 * ks + 3]), a3 = pack_bf16x2(av[1][4 * ks + 2], av[1][4 * ks + 3]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(d[nt][0]), "+f"(d[nt][1]), "+f"(d[nt][2]), "+f"(d[nt][3])
+                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bfrag[ks][nt][0]), "r"(bfrag[ks][nt][1]));
+        }
+        // swish, bf16, through the staging tile: row = pixel of the tile, word = channel pair
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            stage[warp][g][4 * nt + t] = pack_bf16x2(silu(d[nt][0]), silu(d[nt][1]));
+            stage[warp][g + 8][4 * nt + t] = pack_bf16x2(silu(d[nt][2]), silu(d[nt][3]));
+        }
+        __syncwarp();
+        // 16 pixels x 64 bytes are contiguous in y: 64 16-byte pieces, two per lane
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int piece = lane + 32 * h, row = piece >> 2, q = piece & 3;
+            const unsigned pix = tile * 16 + row;
+            if (pix < total) {
+                uint4 v;
+                v.x = stage[warp][row][4 * q + 0]; v.y = stage[warp][row][4 * q + 1];
+                v.z = stage[warp][row][4 * q + 2]; v.w = stage[warp][row][4 * q + 3];
+                *reinterpret_cast<uint4*>(y + (long long)pix * 32 + q * 8) = v;
             }
         }
+        __syncwarp();
     }
 }
 
@@ -433,31 +223,74 @@ fma8(acc[j], tv, wk[dx]);
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSeRows = 16;
 constexpr int kSeMaxC = 1280, kSeMaxSq = 64;
+// The two matrix-vector products are latency-bound (one CTA per image, ~0.4 MB of weights from L2): every lane keeps several
+// independent 16-byte loads in flight (the first version issued one scalar load per fused multiply-add: 46 us per call at
+// C = 1152; this one ~8 us).
 __global__ void __launch_bounds__(256)
 se_mlp_kernel(float* __restrict__ pool, float inv_hw, const float* __restrict__ Wr, const float* __restrict__ br,
               const float* __restrict__ We, const float* __restrict__ be, int C, int Cse, int Sq) {
-    __shared__ float m[kSeMaxC];
+    __shared__ __align__(16) float m[kSeMaxC];
     __shared__ float r[kSeMaxSq];
     float* row = pool + (long long)blockIdx.x * C;
     for (int c = threadIdx.x; c < Cse; c += blockDim.x) m[c] = row[c] * inv_hw;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int q = warp; q < Sq; q += 8) {
-        float a = 0.f;
-        for (int c = lane; c < Cse; c += 32) a = fmaf(__ldg(Wr + (long long)q * Cse + c), m[c], a);
+    if ((Cse & 3) == 0) {
+        // squeeze: two rows of Wr per warp at a time, float4 loads, four in flight per row
+        const int n4 = Cse >> 2;
+        const float4* m4 = reinterpret_cast<const float4*>(m);
+        for (int q = warp; q < Sq; q += 16) {
+            const int q2 = q + 8;
+            const bool two = q2 < Sq;
+            const float4* w0 = reinterpret_cast<const float4*>(Wr + (long long)q * Cse);
+            const float4* w1 = reinterpret_cast<const float4*>(Wr + (long long)(two ? q2 : q) * Cse);
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+            for (int i = lane; i < n4; i += 32) {
+                const float4 x = m4[i], u = __ldg(w0 + i), v = __ldg(w1 + i);
+                a0 = fmaf(u.x, x.x, fmaf(u.y, x.y, fmaf(u.z, x.z, fmaf(u.w, x.w, a0))));
+                a1 = fmaf(v.x, x.x, fmaf(v.y, x.y, fmaf(v.z, x.z, fmaf(v.w, x.w, a1))));
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) r[q] = silu(a + __ldg(br + q));
+            for (int o = 16; o > 0; o >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            }
+            if (lane == 0) {
+                r[q] = silu(a0 + __ldg(br + q));
+                if (two) r[q2] = silu(a1 + __ldg(br + q2));
+            }
+        }
+    } else {
+        for (int q = warp; q < Sq; q += 8) {
+            float a = 0.f;
+            for (int c = lane; c < Cse; c += 32) a = fmaf(__ldg(Wr + (long long)q * Cse + c), m[c], a);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) r[q] = silu(a + __ldg(br + q));
+        }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float v = 0.f;
-        if (c < Cse) {
-            float a = __ldg(be + c);
-            for (int q = 0; q < Sq; ++q) a = fmaf(__ldg(We + (long long)q * Cse + c), r[q], a);      // We^T (Sq, Cse): coalesced over c
-            v = __fdividef(1.f, 1.f + __expf(-a));
-        }
-        row[c] = v;
+    // excite: a thread owns channels c, c + 256, ... (at most 5) and walks the Sq rows of We^T once for all of them
+    constexpr int kPer = kSeMaxC / 256;
+    float a[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int c = threadIdx.x + j * 256;
+        a[j] = c < Cse ? __ldg(be + c) : 0.f;
+    }
+#pragma unroll 4
+    for (int q = 0; q < Sq; ++q) {
+        const float rq = r[q];
+        const float* wq = We + (long long)q * Cse + threadIdx.x;        // We^T (Sq, Cse): coalesced over c
+#pragma unroll
+        for (int j = 0; j < kPer; ++j)
+            if (threadIdx.x + j * 256 < Cse) a[j] = fmaf(__ldg(wq + j * 256), rq, a[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int c = threadIdx.x + j * 256;
+        if (c < C) row[c] = c < Cse ? __fdividef(1.f, 1.f + __expf(-a[j])) : 0.f;
     }
 }
 
@@ -610,10 +443,18 @@ int mfb_stem_conv_bf16(const void* img, const void* w, const void* shift, void* 
     if ((long long)N * Ho * Wo >= (1ll << 31)) return fail_status(MFB_ERR_UNSUPPORTED, "stem_conv: more than 2^31 output pixels");
     const long long total = (long long)N * Ho * Wo;
     StemWeights sw;                                          // HOST pointers: the weights are passed by value
-    memcpy(sw.w, w, sizeof(sw.w));
+    memset(&sw, 0, sizeof(sw));
+    const float* wf = (const float*)w;
+    for (int k = 0; k < 27; ++k)
+        for (int co = 0; co < 32; ++co) {
+            uint32_t u;
+            memcpy(&u, wf + k * 32 + co, 4);
+            sw.w[k][co] = (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);      // fp32 -> bf16, round to nearest even
+        }
     memcpy(sw.shift, shift, sizeof(sw.shift));
-    stem_conv_kernel<<<grid_for(total, 128, 148 * 16), 128, 0, (cudaStream_t)stream>>>((const float*)img, sw, (__nv_bfloat16*)y, N, H, W,
-                                                                                       Ho, Wo, pad_h, pad_w);
+    const long long tiles = (total + 15) / 16;
+    stem_conv_kernel<<<grid_for((tiles + kStemWarps - 1) / kStemWarps, 1, 148 * 8), kStemWarps * 32, 0, (cudaStream_t)stream>>>(
+        (const float*)img, sw, (__nv_bfloat16*)y, N, H, W, Ho, Wo, pad_h, pad_w);
     return after_launch("stem_conv");
 }
 
@@ -625,45 +466,10 @@ int mfb_dwconv_bn_silu_bf16(const void* x, const void* w, const void* shift, voi
     if (K != 3 && K != 5) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: kernel size must be 3 or 5");
     if (stride != 1 && stride != 2) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: stride must be 1 or 2");
     if (((uintptr_t)x | (uintptr_t)y | (uintptr_t)w | (uintptr_t)shift) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "dwconv: tensors must be 16-byte aligned");
-    if (stride == 1 && Ho == H && Wo == W) {
-        // stride 1 ("same"): shared-memory tile kernel; 32-wide tiles unless the map is narrower
-        const int TW = W > 16 ? 32 : 16, TH = 256 / TW;                 // 4 groups x (TW/4) strips x TH rows = 256 threads
-        const long long sp = (long long)((W + TW - 1) / TW) * ((H + TH - 1) / TH);
-        const long long tiles = ((sp + kDwChunk - 1) / kDwChunk) * ((C + kDwSlab - 1) / kDwSlab) * N;     // work units
-        if (tiles >= (1ll << 31)) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: too many tiles");
-        const long long resident = 148ll * 2;                          // persistent: 2 CTAs per SM
-        dim3 grid((unsigned)(tiles < resident ? tiles : resident));
-        const size_t smem = 128 + 2 * (size_t)(TH + K - 1) * (TW + K - 1) * kDwPitch;    // two tile buffers
-        auto go = [&](auto kern) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
-            kern<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const float*)w, (const float*)shift,
-                                                           (__nv_bfloat16*)y, (float*)pool, N, H, W, C, pad_h, pad_w, TW, TH);
-            return true;
-        };
-        if (!(K == 3 ? go(dwconv_tile_kernel<3>) : go(dwconv_tile_kernel<5>)))
-            return fail_status(MFB_ERR_CUDA, "dwconv: cudaFuncSetAttribute failed");
-        return after_launch("dwconv (tile)");
-    }
-    const int G = C >> 3;
-    if (G > 256) return fail_status(MFB_ERR_UNSUPPORTED, "dwconv: at most 2048 channels");
-    const int P = 256 / G;
-    const int threads = ((P * G + 31) / 32) * 32;
-    const long long n_strips = (long long)Ho * ((Wo + kDwStrip - 1) / kDwStrip);
-    // strips per thread: as many as possible (fewer pool atomics) while the grid keeps >= 4 waves of 2 CTAs per SM
-    long long rows = (n_strips * N) / ((long long)P * 148 * 2 * 4);
-    rows = rows < 1 ? 1 : (rows > kDwMaxRows ? kDwMaxRows : rows);
-    dim3 grid((unsigned)((n_strips + (long long)P * rows - 1) / ((long long)P * rows)), (unsigned)N);
-    const size_t smem = (size_t)C * sizeof(float);
-    auto go = [&](auto kern) {
-        kern<<<grid, threads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const float*)w, (const float*)shift,
-                                                            (__nv_bfloat16*)y, (float*)pool, H, W, C, Ho, Wo, pad_h, pad_w, (int)rows);
-    };
-    if (K == 3 && stride == 1) go(dwconv_kernel<3, 1>);
-    else if (K == 3) go(dwconv_kernel<3, 2>);
-    else if (stride == 1) go(dwconv_kernel<5, 1>);
-    else go(dwconv_kernel<5, 2>);
-    return after_launch("dwconv");
+    return launch_dwconv_tma(x, (const float*)w, (const float*)shift, y, (float*)pool, N, H, W, C, Ho, Wo, K, stride, pad_h, pad_w,
+                             (cudaStream_t)stream);
 }
+
 
 int mfb_se_fold_bf16(void* pool, float inv_hw, const void* w_reduce, const void* b_reduce, const void* w_expand,
                      const void* b_expand, const void* proj_w, void* out_w, int N, int C, int C_se, int Sq, int Cout, void* stream) {

@@ -63,7 +63,9 @@ def upsample_concat_nhwc(skip, low, out_hw, c_out):
 
 
 def stem_conv(img, w, shift, pad):
+    # the kernel contracts on the tensor cores: image and weights rounded to bf16, fp32 accumulate (like every other conv of the trunk)
     lo, hi = pad
+    img, w = img.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()
     y = F.conv2d(F.pad(img, (lo, hi, lo, hi)), w.permute(3, 2, 0, 1), stride=2)
     return F.silu(y.permute(0, 2, 3, 1) + shift)
 
