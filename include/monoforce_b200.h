@@ -122,7 +122,11 @@ typedef struct mfb_rollout_grads {
  * 8-scalar corner-gradient record. */
 int64_t mfb_rollout_workspace_bytes(const mfb_rollout_desc* desc, int dtype);
 
-/* Replaces DPhysics.dphysics (dphysics.py:530-594): snap, T fused steps, post-processing. */
+/* Replaces DPhysics.dphysics (dphysics.py:530-594): snap, T fused steps, post-processing.
+ * Two kernels implement it: one warp per trajectory (large batches) and one CTA per trajectory
+ * (batches below 512 trajectories, 1024 for the odeint variant; never with joint_angles).  The
+ * environment variable MFB_FWD_WIDE_MAX_B overrides that threshold (0 = always one warp per
+ * trajectory); the two agree to fp32 round-off (the per-step sums are associated differently). */
 int mfb_rollout_forward(const mfb_rollout_desc* desc, const mfb_rollout_buffers* io,
                         int dtype, void* stream);
 
