@@ -14,8 +14,8 @@ forward, overlapping the adjoint) and the two map gradients all-reduced over NCC
 
 Prints ONE JSON line (rank 0).  Besides the contract keys the line carries the other BASELINE configs as
 extra blocks: `forward_only` (config 2), `encoder_cfg4` + `cfg4_e2e` (config 4), `cfg5` (config 5, at --gpus 8),
-`strong_scaling` (N > 1), `reference_published` (the one timing the reference publishes), `odeint` (the callers'
-default integrator at config 2/3 size), `small_batch` latencies and `shooting_e2e`.
+`strong_scaling` (N > 1), `reference_published` / `encoder_published` (the two timings the reference publishes), `odeint`
+(the callers' default integrator at config 2/3 size), `small_batch` latencies and `shooting_e2e`.
 `--impl reference` times the CPU restatement of the reference (oracle/, proven bit-identical to the
 reference's PyTorch-CPU DPhysics) on a bounded sample.
 """
@@ -432,6 +432,36 @@ def block_encoder(dev, steps, cfg4, peaks):
     return res, net, host, calib
 
 
+def block_encoder_published(dev, steps):
+    """The reference's other published number: LiftSplatShoot forward on ONE scene (4 cameras 256x416 -> 128x128 BEV, lss_cfg.yaml),
+    0.391 s for the first call in monoforce/examples/monoforce_inference_with_rough_data.ipynb:392.
+    Here: latency of one forward with the images coming from pinned host memory and the terrain map read back, eager launches
+    and CUDA-graph replay."""
+    from helpers_lss import default_cfg, make_inputs
+    from monoforce_b200 import LiftSplatShoot
+    import warnings
+    gc, ac = default_cfg()
+    torch.manual_seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = LiftSplatShoot(gc, ac).to(dev).eval()
+    net.fast_inference = True
+    host = [t.pin_memory() for t in make_inputs(gc, ac, 1, 0)]
+    calib = [t.to(dev) for t in host[1:]]
+
+    def call():
+        with torch.no_grad():
+            out = net(host[0].to(dev, non_blocking=True), *calib)
+            return out["terrain"].cpu()                      # 64 KB back to the host: a blocking caller's view
+    eager = wall_ms(call, max(steps, 10))
+    net.fast_graph = True
+    graph = wall_ms(call, max(steps, 10))
+    return {"workload": "monoforce_inference_with_rough_data.ipynb: LiftSplatShoot forward, 1 scene x 4 cams 256x416 -> 128x128 BEV, eval; "
+                        "images from pinned host memory, terrain map read back; host wall clock incl. synchronize, median",
+            "published_s_first_call": 0.391, "published_hardware": "unspecified CUDA GPU (notebook output, first call incl. warm-up)",
+            "ms_eager_launches": eager["median_ms"], "ms_graph_replay": graph["median_ms"], "min_ms": graph["min_ms"]}
+
+
 def block_cfg4_e2e(dev, steps, net, host, calib):
     """BASELINE config 4 end to end: images (host) -> encoder -> terrain / friction maps -> 16 scenes x 256 control
     sequences (one map per scene, map groups) -> fused costs -> host."""
@@ -721,6 +751,8 @@ def main():
             res4, net4, host4, calib4 = block_encoder(dev, args.steps, True, peaks)
             extras["encoder_cfg4"] = res4
             extras["cfg4_e2e"] = guarded(lambda: block_cfg4_e2e(dev, args.steps, net4, host4, calib4))
+            del net4, host4, calib4
+            extras["encoder_published"] = guarded(lambda: block_encoder_published(dev, args.steps))
             return True
         r = guarded(enc_blocks)
         if r is not True:

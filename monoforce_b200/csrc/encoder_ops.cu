@@ -251,73 +251,59 @@ stem_conv_kernel(const float* __restrict__ img, const __grid_constant__ StemWeig
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSeRows = 16;
 constexpr int kSeMaxC = 1280, kSeMaxSq = 64;
-// The two matrix-vector products are latency-bound (one CTA per image, ~0.4 MB of weights from L2): every lane keeps several
-// independent 16-byte loads in flight (the first version issued one scalar load per fused multiply-add: 46 us per call at
-// C = 1152; this one ~8 us).
-__global__ void __launch_bounds__(256)
+// The two matrix-vector products are latency-bound (one CTA per image, ~0.4 MB of weights from L2 / HBM, a few images in
+// flight): what counts is the number of loads in flight, so the CTA is 1024 threads and every lane issues 16-byte loads
+// back to back (the first version, 256 threads and one scalar load per fused multiply-add, took 46-66 us per call at
+// C = 1152).
+constexpr int kSeThreads = 1024;
+__global__ void __launch_bounds__(kSeThreads)
 se_mlp_kernel(float* __restrict__ pool, float inv_hw, const float* __restrict__ Wr, const float* __restrict__ br,
               const float* __restrict__ We, const float* __restrict__ be, int C, int Cse, int Sq) {
     __shared__ __align__(16) float m[kSeMaxC];
     __shared__ float r[kSeMaxSq];
     float* row = pool + (long long)blockIdx.x * C;
-    for (int c = threadIdx.x; c < Cse; c += blockDim.x) m[c] = row[c] * inv_hw;
+    for (int c = threadIdx.x; c < Cse; c += kSeThreads) m[c] = row[c] * inv_hw;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if ((Cse & 3) == 0) {
-        // squeeze: two rows of Wr per warp at a time, float4 loads, four in flight per row
-        const int n4 = Cse >> 2;
-        const float4* m4 = reinterpret_cast<const float4*>(m);
-        for (int q = warp; q < Sq; q += 16) {
-            const int q2 = q + 8;
-            const bool two = q2 < Sq;
-            const float4* w0 = reinterpret_cast<const float4*>(Wr + (long long)q * Cse);
-            const float4* w1 = reinterpret_cast<const float4*>(Wr + (long long)(two ? q2 : q) * Cse);
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
+    // squeeze: one row of Wr per warp
+    for (int q = warp; q < Sq; q += kSeThreads / 32) {
+        float a = 0.f;
+        if ((Cse & 3) == 0) {
+            const int n4 = Cse >> 2;
+            const float4* m4 = reinterpret_cast<const float4*>(m);
+            const float4* w4 = reinterpret_cast<const float4*>(Wr + (long long)q * Cse);
+#pragma unroll 10
             for (int i = lane; i < n4; i += 32) {
-                const float4 x = m4[i], u = __ldg(w0 + i), v = __ldg(w1 + i);
-                a0 = fmaf(u.x, x.x, fmaf(u.y, x.y, fmaf(u.z, x.z, fmaf(u.w, x.w, a0))));
-                a1 = fmaf(v.x, x.x, fmaf(v.y, x.y, fmaf(v.z, x.z, fmaf(v.w, x.w, a1))));
+                const float4 x = m4[i], u = __ldg(w4 + i);
+                a = fmaf(u.x, x.x, fmaf(u.y, x.y, fmaf(u.z, x.z, fmaf(u.w, x.w, a))));
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-            }
-            if (lane == 0) {
-                r[q] = silu(a0 + __ldg(br + q));
-                if (two) r[q2] = silu(a1 + __ldg(br + q2));
-            }
-        }
-    } else {
-        for (int q = warp; q < Sq; q += 8) {
-            float a = 0.f;
+        } else {
             for (int c = lane; c < Cse; c += 32) a = fmaf(__ldg(Wr + (long long)q * Cse + c), m[c], a);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) r[q] = silu(a + __ldg(br + q));
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) r[q] = silu(a + __ldg(br + q));
     }
     __syncthreads();
-    // excite: a thread owns channels c, c + 256, ... (at most 5) and walks the Sq rows of We^T once for all of them
-    constexpr int kPer = kSeMaxC / 256;
+    // excite: a thread owns channels c, c + 1024 and walks the Sq rows of We^T (Sq, Cse; coalesced over c) once for both
+    constexpr int kPer = (kSeMaxC + kSeThreads - 1) / kSeThreads;
     float a[kPer];
 #pragma unroll
     for (int j = 0; j < kPer; ++j) {
-        const int c = threadIdx.x + j * 256;
+        const int c = threadIdx.x + j * kSeThreads;
         a[j] = c < Cse ? __ldg(be + c) : 0.f;
     }
-#pragma unroll 4
+#pragma unroll 8
     for (int q = 0; q < Sq; ++q) {
         const float rq = r[q];
-        const float* wq = We + (long long)q * Cse + threadIdx.x;        // We^T (Sq, Cse): coalesced over c
+        const float* wq = We + (long long)q * Cse + threadIdx.x;
 #pragma unroll
         for (int j = 0; j < kPer; ++j)
-            if (threadIdx.x + j * 256 < Cse) a[j] = fmaf(__ldg(wq + j * 256), rq, a[j]);
+            if (threadIdx.x + j * kSeThreads < Cse) a[j] = fmaf(__ldg(wq + j * kSeThreads), rq, a[j]);
     }
 #pragma unroll
     for (int j = 0; j < kPer; ++j) {
-        const int c = threadIdx.x + j * 256;
+        const int c = threadIdx.x + j * kSeThreads;
         if (c < C) row[c] = c < Cse ? __fdividef(1.f, 1.f + __expf(-a[j])) : 0.f;
     }
 }
@@ -505,7 +491,7 @@ int mfb_se_fold_bf16(void* pool, float inv_hw, const void* w_reduce, const void*
     if (N < 1 || Cout < 1 || Sq < 1 || Sq > kSeMaxSq || C < 8 || C > kSeMaxC || (C & 7) || C_se < 1 || C_se > C)
         return fail_status(MFB_ERR_UNSUPPORTED, "se_fold: need C % 8 == 0, C <= 1280, Sq <= 64, C_se <= C");
     if ((uintptr_t)pool & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "se_fold: pool must be 16-byte aligned");
-    se_mlp_kernel<<<(unsigned)N, 256, 0, (cudaStream_t)stream>>>((float*)pool, inv_hw, (const float*)w_reduce, (const float*)b_reduce,
+    se_mlp_kernel<<<(unsigned)N, kSeThreads, 0, (cudaStream_t)stream>>>((float*)pool, inv_hw, (const float*)w_reduce, (const float*)b_reduce,
                                                                  (const float*)w_expand, (const float*)b_expand, C, C_se, Sq);
     if (int rc = after_launch("se_mlp")) return rc;
     dim3 grid((unsigned)((Cout + kSeRows - 1) / kSeRows), (unsigned)N);

@@ -1,4 +1,4 @@
-"""One warm + N profiled encoder forwards (fast path) for ncu launch lists:  python tools/encoder_once.py [--cfg4] [n]"""
+"""One warm + N profiled encoder forwards (fast path) for ncu launch lists:  python tools/encoder_once.py [--cfg4] [--b1] [n]"""
 import os
 import sys
 import warnings
@@ -19,7 +19,7 @@ with warnings.catch_warnings():
     warnings.simplefilter("ignore")
     net = LiftSplatShoot(gc, ac).cuda().eval()
 net.fast_inference = True
-inputs = [t.cuda() for t in make_inputs(gc, ac, 16, 0)]
+inputs = [t.cuda() for t in make_inputs(gc, ac, 1 if "--b1" in sys.argv else 16, 0)]
 with torch.no_grad():
     for _ in range(1 + n):
         net(*inputs)
