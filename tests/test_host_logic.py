@@ -111,6 +111,30 @@ def test_module_surface_and_no_cpu_fallback():
         sim(cfg.z_grid.repeat(3, 1, 1), controls[:2], state=state)
 
 
+def test_per_call_attributes_and_default_friction_cache():
+    """Host-side shortcuts of the planner's latency path keep the module's semantics: per-call tensors are plain attributes
+    (never parameters / buffers, so state_dict is unchanged), everything else still goes through nn.Module.__setattr__, and
+    the cached device copy of dphys_cfg.friction follows in-place edits and replacement of the config tensor."""
+    from monoforce_b200 import DPhysics, DPhysConfig
+    cfg = DPhysConfig(robot="tradr", grid_res=0.4)
+    sim = DPhysics(cfg, device="cpu")
+    sim.controls = torch.zeros(2, 5, 2)
+    sim.z_grid = torch.nn.Parameter(torch.zeros(1, 4, 4))              # even a Parameter stays a plain per-call attribute
+    assert "controls" in sim.__dict__ and "z_grid" in sim.__dict__ and len(list(sim.parameters())) == 0
+    assert len(sim.state_dict()) == 0
+    sim.extra = torch.nn.Parameter(torch.ones(3))                      # anything else is registered as usual
+    assert [n for n, _ in sim.named_parameters()] == ["extra"]
+    f0 = sim._default_friction()
+    assert f0.shape == (1,) + tuple(cfg.friction.shape) and sim._default_friction() is f0          # cached
+    cfg.friction.mul_(0.5)                                             # in-place edit bumps the tensor version
+    f1 = sim._default_friction()
+    assert f1 is not f0 and torch.equal(f1[0], cfg.friction)
+    cfg.friction = torch.full_like(cfg.friction, 0.3)                  # replaced tensor
+    assert torch.equal(sim._default_friction()[0], cfg.friction)
+    z = sim._zero_scalar(torch.float32).expand(2, 5, 4)
+    assert z.shape == (2, 5, 4) and z.stride() == (0, 0, 0) and float(z.abs().sum()) == 0.0
+
+
 def test_unsupported_integration_mode_is_refused_not_run_as_euler():
     """ADVICE r1: the reference honours integration_mode ('rk4' in update_state :361-383, `method=` of odeint :510-511);
     the kernels are Euler only, so any other mode must raise instead of silently producing Euler trajectories."""

@@ -846,7 +846,8 @@ def _custom_robot(n_points, seed=0):
 
 @pytest.mark.parametrize("n_points,B,T,variant", [
     (1, 1, 1, "step"), (5, 3, 2, "step"), (31, 5, 3, "odeint"), (32, 2, 5, "step"), (33, 7, 7, "odeint"),
-    (64, 9, 6, "step"), (100, 4, 9, "step"), (161, 6, 5, "odeint"), (200, 3, 11, "step"), (256, 5, 4, "step"),
+    (64, 9, 6, "step"), (65, 2, 4, "odeint"), (100, 4, 9, "step"), (129, 3, 5, "step"), (161, 6, 5, "odeint"), (200, 3, 11, "step"),
+    (256, 5, 4, "step"),        # 65 / 129: first sizes that need a second / third warp in the one-CTA-per-trajectory forward kernel
 ])
 def test_ragged_sizes_fp64_forward_and_adjoint(n_points, B, T, variant, adjoint_kernel):
     """Edge sizes: 1..256 contact points (all PPL instantiations), batch not a multiple of the CTA size, horizons
