@@ -104,6 +104,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "}\n" : "=r"(done) : "r"(s_addr(bar)), "r"(parity) : "memory");
     }
 }
+// Same wait for the two single-thread roles (TMA producer waiting for a free stage, MMA issuer waiting for a drained
+// accumulator): between polls the thread sleeps, so that on the memory-bound layers - where both of them wait for the
+// epilogue most of the time - their polling does not take issue slots from the eight epilogue warps (ncu, MBConv block-1
+// expand: a quarter of all issued instructions were these two loops).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(s_addr(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(40);
+    }
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  :: "r"(s_addr(dst)), "l"(map), "r"(s_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -180,12 +197,15 @@ __device__ __forceinline__ float erf_fast(float x) {
     return copysignf(fmaf(-poly, e, 1.f), x);
 }
 
+// Activation of u = kActPre<ACT> * (acc * scale + shift): for SiLU the epilogue works on h = x / 2 (the factor is folded into
+// the staged scale / shift), x sigmoid(x) = h + h tanh(h): one FMA + one SFU op per element instead of FMUL + FMA + SFU.
+template <int ACT> constexpr float kActPre = ACT == kSilu ? 0.5f : 1.f;
 template <int ACT>
-__device__ __forceinline__ float apply_act(float v) {
-    if (ACT == kRelu) return fmaxf(v, 0.f);
-    if (ACT == kGelu) return 0.5f * v * (1.f + erf_fast(v * 0.70710678118654752f));      // nn.GELU() (erf form)
-    if (ACT == kSilu) { const float h = 0.5f * v; return fmaf(h, tanh_approx(h), h); }   // x sigmoid(x) = x/2 (1 + tanh(x/2))
-    return v;
+__device__ __forceinline__ float apply_act(float u) {
+    if (ACT == kRelu) return fmaxf(u, 0.f);
+    if (ACT == kGelu) return 0.5f * u * (1.f + erf_fast(u * 0.70710678118654752f));      // nn.GELU() (erf form)
+    if (ACT == kSilu) return fmaf(u, tanh_approx(u), u);
+    return u;
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -236,8 +256,8 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     float* s_head = s_shift + kMaxParamChannels;
     for (int i = threadIdx.x; i < n_blocks * BLOCK_N; i += kThreads) {
         const bool in = i < p.Cout;
-        s_scale[i] = in ? __ldg(p.scale + i) : 1.f;
-        s_shift[i] = in ? __ldg(p.shift + i) : 0.f;
+        s_scale[i] = in ? kActPre<ACT> * __ldg(p.scale + i) : 1.f;
+        s_shift[i] = in ? kActPre<ACT> * __ldg(p.shift + i) : 0.f;
         if (HEAD) s_head[i] = in ? __ldg(p.head_w + i) : 0.f;
     }
     tc_fence_before();
@@ -257,7 +277,7 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 const int w0 = tw * kTileW, h0 = th * kTileH, n0 = nb * BLOCK_N;
                 for (int i = 0; i < k_iters; ++i, ++it) {
                     const int s = it % kStages;
-                    mbar_wait(empty + s, ((it / kStages) & 1) ^ 1);
+                    mbar_wait_relaxed(empty + s, ((it / kStages) & 1) ^ 1);
                     const int tap = i / chunks_per_tap, c0 = (i - tap * chunks_per_tap) * kBlockK;
                     const int dy = tap / p.KW, dx = tap - dy * p.KW;
                     uint8_t* a_dst = smem + s * S::kStageBytes;
@@ -278,7 +298,7 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
             uint32_t it = 0, lt = 0;
             for (unsigned t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
                 const uint32_t as = lt & 1;
-                mbar_wait(acc_empty + as, ((lt >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
+                mbar_wait_relaxed(acc_empty + as, ((lt >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + as * BLOCK_N;
                 for (int i = 0; i < k_iters; ++i, ++it) {
@@ -365,17 +385,32 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                                 const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
                                 float v[8];
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] = fmaf(__uint_as_float(r[8 * g8 + j]), sc[j], sh[j]);
+                                for (int j = 0; j < 8; j += 2) {           // packed f32x2: the accumulator columns arrive as register pairs
+                                    const float2 a2 = make_float2(__uint_as_float(r[8 * g8 + j]), __uint_as_float(r[8 * g8 + j + 1]));
+                                    const float2 v2 = __ffma2_rn(a2, make_float2(sc[j], sc[j + 1]), make_float2(sh[j], sh[j + 1]));
+                                    v[j] = v2.x; v[j + 1] = v2.y;
+                                }
                                 if (rsd) {
                                     const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rsd + c + 8 * g8));
                                     const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(r2[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float2 f = __bfloat1622float2(r2[j]);
+                                        v[2 * j] = fmaf(kActPre<ACT>, f.x, v[2 * j]); v[2 * j + 1] = fmaf(kActPre<ACT>, f.y, v[2 * j + 1]);
+                                    }
                                 }
                                 uint32_t pk[4];
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(apply_act<ACT>(v[2 * j]), apply_act<ACT>(v[2 * j + 1]));
+                                    float o0, o1;
+                                    if (ACT == kSilu) {
+                                        const float2 u2 = make_float2(v[2 * j], v[2 * j + 1]);
+                                        const float2 o2 = __ffma2_rn(u2, make_float2(tanh_approx(u2.x), tanh_approx(u2.y)), u2);
+                                        o0 = o2.x; o1 = o2.y;
+                                    } else {
+                                        o0 = apply_act<ACT>(v[2 * j]); o1 = apply_act<ACT>(v[2 * j + 1]);
+                                    }
+                                    const __nv_bfloat162 b2 = __floats2bfloat162_rn(o0, o1);
                                     pk[j] = *reinterpret_cast<const uint32_t*>(&b2);
                                 }
                                 if (XPOSE) *reinterpret_cast<uint4*>(xbuf + lane * kXposePitch + g8 * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

@@ -16,9 +16,14 @@ def timed(fn, n=10):
     return a.elapsed_time(b) / n
 
 dev = "cuda"
-for name, (N, H, W, Cin, Cout, act) in {"b1_expand 16->96 @256": (64, 256, 256, 16, 96, ops.ACT_SILU), "b2_expand 24->144 @128": (64, 128, 128, 24, 144, ops.ACT_SILU),
+only = [a for a in sys.argv[1:] if not a.startswith("-")]
+for name, (N, H, W, Cin, Cout, act) in {"b1_expand folded x4: 64->384 @256x64": (64, 256, 64, 64, 384, ops.ACT_SILU),
+                                      "b2_expand folded x4: 96->576 @128x32": (64, 128, 32, 96, 576, ops.ACT_SILU),
+                                      "b1_expand 16->96 @256": (64, 256, 256, 16, 96, ops.ACT_SILU), "b2_expand 24->144 @128": (64, 128, 128, 24, 144, ops.ACT_SILU),
                                       "64->96 @256 (full K chunk)": (64, 256, 256, 64, 96, ops.ACT_SILU), "16->128 @256": (64, 256, 256, 16, 128, ops.ACT_SILU),
                                       "b0_project 32->16 @256": (64, 256, 256, 32, 16, ops.ACT_NONE)}.items():
+    if only and not any(o in name for o in only):
+        continue
     x = torch.randn(N, H, W, Cin, device=dev).to(torch.bfloat16)
     w = (torch.randn(Cout, 1, 1, Cin, device=dev) * 0.1).to(torch.bfloat16)
     sc, sh = torch.ones(Cout, device=dev), torch.zeros(Cout, device=dev)
