@@ -44,9 +44,9 @@ static int sm_count() {
     return cached[dev];
 }
 
-template <int BLOCK_N, int ACT, bool HEAD, int STAGES, bool XPOSE>
+template <int BLOCK_N, int ACT, bool HEAD, int STAGES, bool XPOSE, bool RES>
 static int launch_v(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p, cudaStream_t st) {
-    auto kern = conv_bn_act_kernel<BLOCK_N, ACT, HEAD, STAGES, XPOSE>;
+    auto kern = conv_bn_act_kernel<BLOCK_N, ACT, HEAD, STAGES, XPOSE, RES>;
     const int smem = Smem<BLOCK_N, STAGES, XPOSE>::kTotal;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
         return fail_status(MFB_ERR_CUDA, "conv: cudaFuncSetAttribute failed");
@@ -65,8 +65,14 @@ static int launch_v(const CUtensorMap& mx, const CUtensorMap& mw, const Params& 
 template <int BLOCK_N, int ACT, bool HEAD>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p, cudaStream_t st) {
     const int k_iters = p.KH * p.KW * ((p.Cin + kBlockK - 1) / kBlockK);
-    if (!HEAD && k_iters <= 18) return launch_v<BLOCK_N, ACT, false, 2, true>(mx, mw, p, st);
-    return launch_v<BLOCK_N, ACT, HEAD, 3, false>(mx, mw, p, st);
+    // the residual epilogue is a separate instantiation (in the network: MBConv project + identity, ResNet BasicBlock + ReLU)
+    constexpr bool kResOk = !HEAD;
+    if (kResOk && p.res) {
+        if (k_iters <= 18) return launch_v<BLOCK_N, ACT, false, 2, true, kResOk>(mx, mw, p, st);
+        return launch_v<BLOCK_N, ACT, false, 3, false, kResOk>(mx, mw, p, st);
+    }
+    if (!HEAD && k_iters <= 18) return launch_v<BLOCK_N, ACT, false, 2, true, false>(mx, mw, p, st);
+    return launch_v<BLOCK_N, ACT, HEAD, 3, false, false>(mx, mw, p, st);
 }
 
 }  // namespace conv
@@ -136,7 +142,6 @@ extern "C" int mfb_conv2d_bf16(const mfb_conv_desc* d, const void* x, const void
     p.tiles_w = (d->Wo + kTileW - 1) / kTileW;
     p.tiles_h = (d->Ho + kTileH - 1) / kTileH;
     p.per_image_w = d->per_image_weights ? 1 : 0;
-    { const char* dbg = getenv("MFB_CONV_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     p.y = (__nv_bfloat16*)y; p.res = (const __nv_bfloat16*)residual;
     p.scale = (const float*)scale; p.shift = (const float*)shift;
     p.head_out = head ? (float*)head_out : nullptr;

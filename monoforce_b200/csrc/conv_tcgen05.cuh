@@ -53,9 +53,6 @@ struct Params {
     int KH, KW, stride, pad_h, pad_w, act;
     int tiles_w, tiles_h;
     int per_image_w;               // weights are (N, Cout, KH*KW*Cin): the CTA's image selects the matrix
-    int debug;                     // development only (MFB_CONV_DEBUG, tools/conv_experiment.py): bit 0 = skip the transposed global
-                                   // stores, bit 1 = skip the TMEM loads (that experiment showed neither was the limiter of the
-                                   // narrow-input 1x1 layers: 32-byte TMA rows were; see encoder_fast._fold_pixels)
     __nv_bfloat16* y;              // nullptr in head mode
     const __nv_bfloat16* res;      // residual added before the activation, or nullptr
     const float* scale;
@@ -217,7 +214,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Three pipelines (guide: "canonical Blackwell GEMM"): smem full/empty (TMA <-> MMA, kStages deep, runs across tile
 // boundaries so the next tile's operands stream in during this tile's epilogue), TMEM full/empty (MMA <-> epilogue, two
 // accumulators of BLOCK_N columns: the MMAs of tile i+1 overlap the epilogue of tile i), and the tile walk itself.
-template <int BLOCK_N, int ACT, bool HEAD, int kStages, bool XPOSE>
+template <int BLOCK_N, int ACT, bool HEAD, int kStages, bool XPOSE, bool RES>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -367,13 +364,14 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");      // head_part is free for the next tile
             } else {
                 __nv_bfloat16* out = p.y + pix * p.Cout + n0;
-                const __nv_bfloat16* rsd = p.res ? p.res + pix * p.Cout + n0 : nullptr;
+                // RES is a template parameter: as a run-time test the residual add was compiled into ~64 predicated instructions
+                // per 32 columns that took issue slots in every layer without a residual (the epilogue is issue-bound)
+                const __nv_bfloat16* rsd = RES ? p.res + pix * p.Cout + n0 : nullptr;
 #pragma unroll 1
                 for (int c = c_lo; c < c_lo + kColsPerWarp; c += 32) {
                     if (n0 + c >= p.Cout) break;              // warp-uniform: nothing but padding columns left
                     uint32_t r[32];
-                    if (!(p.debug & 2)) tmem_ld32(tmem_acc + c, r);
-                    else { for (int j = 0; j < 32; ++j) r[j] = lane + j; }
+                    tmem_ld32(tmem_acc + c, r);
                     if (in_image) {
 #pragma unroll
                         for (int g8 = 0; g8 < 4; ++g8) {
@@ -390,7 +388,7 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                                     const float2 v2 = __ffma2_rn(a2, make_float2(sc[j], sc[j + 1]), make_float2(sh[j], sh[j + 1]));
                                     v[j] = v2.x; v[j + 1] = v2.y;
                                 }
-                                if (rsd) {
+                                if (RES) {
                                     const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rsd + c + 8 * g8));
                                     const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
@@ -428,7 +426,7 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                             const int row = 8 * k + (lane >> 2);             // row of this warp's 32 accumulator rows
                             const int mm = q * 32 + row;
                             const int h2 = th * kTileH + mm / kTileW, w2 = tw * kTileW + (mm % kTileW);
-                            if (h2 < p.Ho && w2 < p.Wo && co < p.Cout && !(p.debug & 1)) {
+                            if (h2 < p.Ho && w2 < p.Wo && co < p.Cout) {
                                 const uint4 val = *reinterpret_cast<const uint4*>(xbuf + row * kXposePitch + part * 16);
                                 *reinterpret_cast<uint4*>(p.y + (((long long)n * p.Ho + h2) * p.Wo + w2) * p.Cout + co) = val;
                             }

@@ -1,5 +1,5 @@
 """Where does a memory-bound K4 layer spend its time?  Times MBConv block-1 expand (64 x 256 x 256 x 16 -> 96, 1x1, SiLU) and a few
-other shapes; run under different MFB_CONV_DEBUG values (development switch in the kernel)."""
+other shapes (round 2 used it with a development switch in the kernel that skipped the stores / the TMEM loads; the switch is gone)."""
 import os, sys
 _R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [_R, os.path.join(_R, "tests")]
@@ -29,4 +29,4 @@ for name, (N, H, W, Cin, Cout, act) in {"b1_expand folded x4: 64->384 @256x64": 
     sc, sh = torch.ones(Cout, device=dev), torch.zeros(Cout, device=dev)
     ms = timed(lambda: ops.conv2d_nhwc(x, w, sc, sh, act))
     mb = (x.numel() + N * H * W * Cout) * 2 / 1e6
-    print(f"debug={os.environ.get('MFB_CONV_DEBUG', '0')}  {name:32s} {ms * 1e3:8.1f} us   {mb:7.0f} MB  -> {mb / ms / 1e3:6.2f} TB/s", flush=True)
+    print(f"{name:40s} {ms * 1e3:8.1f} us   {mb:7.0f} MB  -> {mb / ms / 1e3:6.2f} TB/s", flush=True)
