@@ -88,6 +88,7 @@ extern "C" int mfb_conv2d_bf16(const mfb_conv_desc* d, const void* x, const void
     const bool head = d->n_heads > 0;
     if (head ? (!head_w || !head_out) : !y) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: output pointer is NULL");
     if (d->N < 1 || d->H < 1 || d->W < 1 || d->Ho < 1 || d->Wo < 1) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: sizes must be positive");
+    if ((long long)d->N * d->Ho * d->Wo >= (1ll << 31)) return fail_status(MFB_ERR_UNSUPPORTED, "conv: more than 2^31 output pixels");
     if (d->KH < 1 || d->KH > 7 || d->KW < 1 || d->KW > 7) return fail_status(MFB_ERR_UNSUPPORTED, "conv: kernel size must be in [1, 7]");
     if (d->stride != 1 && d->stride != 2) return fail_status(MFB_ERR_UNSUPPORTED, "conv: stride must be 1 or 2");
     if (d->pad_h < 0 || d->pad_w < 0 || d->pad_h >= d->KH || d->pad_w >= d->KW) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: padding must be in [0, K)");

@@ -364,6 +364,17 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                 asm volatile("bar.sync %0, 64;" :: "r"(1 + q) : "memory");      // head_part is free for the next tile
             } else {
                 __nv_bfloat16* out = p.y + pix * p.Cout + n0;
+                // transposed write-out: output pixel of the four accumulator rows this lane stores (-1: outside the image); per tile,
+                // not per 32-column chunk (the 64-bit index arithmetic was ~1.5 instructions per output element)
+                int xrow_pix[4];
+                if (XPOSE) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int mm = q * 32 + 8 * k + (lane >> 2);
+                        const int h2 = th * kTileH + mm / kTileW, w2 = tw * kTileW + (mm % kTileW);
+                        xrow_pix[k] = (h2 < p.Ho && w2 < p.Wo) ? (n * p.Ho + h2) * p.Wo + w2 : -1;
+                    }
+                }
                 // RES is a template parameter: as a run-time test the residual add was compiled into ~64 predicated instructions
                 // per 32 columns that took issue slots in every layer without a residual (the epilogue is issue-bound)
                 const __nv_bfloat16* rsd = RES ? p.res + pix * p.Cout + n0 : nullptr;
@@ -424,11 +435,9 @@ conv_bn_act_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const int row = 8 * k + (lane >> 2);             // row of this warp's 32 accumulator rows
-                            const int mm = q * 32 + row;
-                            const int h2 = th * kTileH + mm / kTileW, w2 = tw * kTileW + (mm % kTileW);
-                            if (h2 < p.Ho && w2 < p.Wo && co < p.Cout) {
+                            if (xrow_pix[k] >= 0 && co < p.Cout) {
                                 const uint4 val = *reinterpret_cast<const uint4*>(xbuf + row * kXposePitch + part * 16);
-                                *reinterpret_cast<uint4*>(p.y + (((long long)n * p.Ho + h2) * p.Wo + w2) * p.Cout + co) = val;
+                                *reinterpret_cast<uint4*>(p.y + (long long)xrow_pix[k] * p.Cout + co) = val;
                             }
                         }
                         __syncwarp();
