@@ -13,9 +13,10 @@
 //     and used by up to K*K outputs from registers; all math is packed f32x2 over the channel pair (FFMA2 / FMUL2 / FADD2);
 //   * the lane's BN-folded taps and shift live in registers (2 K^2 + 2 values), reloaded only when the walk changes slab;
 //   * squeeze-excite sums stay in registers until the walk leaves the (image, slab).
-// Bound: fp32 FMA issue.  FFMA and FFMA2 retire the same 16 FMA / clk / SM sub-partition here (scalar and packed builds
-// measured identical), i.e. 18 TFMA/s for the GPU; the 5x5 layers run at 12-14 TFMA/s, the 3x3 / stride-2 layers sit between
-// that and their HBM time (2.7-4.5 TB/s).  Tensor cores (a banded-Toeplitz formulation) are the next step, not taken.
+// Bound: the 5x5 layers run at 12-14 TFMA/s, a third of the fp32 peak: ncu shows the FMA pipe 48 % busy (an FFMA2 holds it for two
+// cycles) and 51 % of the issue slots used - a scalar-FFMA build ran in exactly the same time, so it is the phase structure of a
+// thread (load + unpack phases idle the pipe, FMA-dense phases saturate it) with 16 warps per SM, not the instruction count.  The
+// 3x3 / stride-2 layers are bound by their loads (2.3-4.5 TB/s).  Tensor cores (a banded-Toeplitz formulation) are the next step.
 #include <cstdint>
 #include <mutex>
 #include <string>
