@@ -313,6 +313,14 @@ def block_small_batch(dev, steps):
             return torch.norm(forces[0], dim=-1).std(dim=-1).std(dim=-1).argmin()
     lat = wall_ms(shoot, max(steps, 10))
     out["ros_shooting_B64_T500_128x128_odeint"] = {**lat, "trajectory_steps_per_s": 64 * 500 / (lat["median_ms"] * 1e-3)}
+    # the same call replayed from a CUDA graph (DPhysics.graphed): the host-side work of a call is paid once
+    run = sim.graphed(z, controls)
+
+    def shoot_graph():
+        states, forces = run(z_grid=z)
+        return torch.norm(forces[0], dim=-1).std(dim=-1).std(dim=-1).argmin()
+    lat = wall_ms(shoot_graph, max(steps, 10))
+    out["ros_shooting_graph_replay"] = {**lat, "trajectory_steps_per_s": 64 * 500 / (lat["median_ms"] * 1e-3)}
 
     cfg2 = DPhysConfig(robot="marv", grid_res=0.4)      # 32x32 maps
     sim2 = DPhysics(cfg2, device=dev)

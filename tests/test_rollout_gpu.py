@@ -532,6 +532,32 @@ def test_forward_kernel_dispatch_by_batch_size(variant, monkeypatch, forward_ker
             assert rel_err(a, b) < tol
 
 
+@pytest.mark.parametrize("variant", ["step", "odeint"])
+def test_graph_replay_of_the_planner_call_matches_eager(variant):
+    """DPhysics.graphed: one captured no_grad call replayed with new maps / controls gives bit-identical states, forces and
+    fused cost to the eager call (same kernels, same launch parameters); repeated map copies are read as one shared map."""
+    T, B = 40, 64
+    sim, cfg = _module("marv", 0.1, T, variant)
+    sim.fused_cost = variant == "step"
+    g = torch.Generator().manual_seed(21)
+    maps = [hill_map(cfg, noise=0.02, seed=k).to(DEV)[None] for k in range(3)]
+    ctrls = [torch.stack([torch.rand(B, 1, generator=g) * 2 - 1, torch.rand(B, 1, generator=g) * 2 - 1], -1).repeat(1, T, 1).to(DEV)
+             for _ in range(2)]
+    run = sim.graphed(maps[0].repeat(B, 1, 1), ctrls[0])                 # what monoforce_node.py passes: B copies of the map
+    for z, u in ((maps[0], ctrls[0]), (maps[1], ctrls[0]), (maps[2], ctrls[1])):
+        st_g, fo_g = run(z_grid=z.repeat(B, 1, 1), controls=u)
+        got = [t.clone() for t in st_g + fo_g]
+        cost_g = None if run.cost is None else run.cost.clone()
+        with torch.no_grad():
+            st_e, fo_e = sim(z, u)
+        for a, b in zip(got, st_e + fo_e):
+            assert torch.equal(a, b)
+        if variant == "step":
+            assert torch.equal(cost_g, sim.last_cost)
+    with pytest.raises(ValueError, match="shape"):
+        run(controls=ctrls[0][:, :-1])
+
+
 def test_per_trajectory_maps_and_off_map_clamp():
     """Distinct map per trajectory (training path) + robots that start outside the map exercise the
     reference's flat-index clamp (dphysics.py:432-435)."""
