@@ -130,7 +130,9 @@ int64_t mfb_rollout_workspace_bytes(const mfb_rollout_desc* desc, int dtype);
 int mfb_rollout_forward(const mfb_rollout_desc* desc, const mfb_rollout_buffers* io,
                         int dtype, void* stream);
 
-/* Replaces autograd's backward through DPhysics.dphysics.  `io` must
+/* Replaces autograd's backward through DPhysics.dphysics.  Like the forward, the
+ * single-sweep adjoint runs in two shapes: one CTA per trajectory up to 512 trajectories, one warp per
+ * trajectory above (environment variable MFB_BWD_WIDE_MAX_B moves the switch, 0 = always one warp).  `io` must
  * hold the forward inputs and the recorded states (Xs, Xds, Rs, Omegas, x0z and, if it was
  * requested, contact_sum) of the same call. */
 int mfb_rollout_backward(const mfb_rollout_desc* desc, const mfb_rollout_buffers* io,

@@ -1,6 +1,7 @@
 // Instantiations + PPL dispatcher of the adjoint rollout kernel (K2) for one
 // (scalar type, integrator variant) pair: -DMFB_INST_T=... -DMFB_INST_VARIANT=...
 #include "launch.h"
+#include <cstdlib>
 #include "rollout_bwd_sweep.cuh"
 
 #ifndef MFB_INST_T
@@ -26,12 +27,21 @@ static LaunchError launch_ppl(const RolloutArgs<T>& a, const AdjointArgs<T>& g, 
     return go(rollout_bwd_kernel<T, PPL, VARIANT, false>);
 }
 
-// single-sweep adjoint (K2s): static geometry + the forward's contact_sum tape
+// single-sweep adjoint (K2s): static geometry + the forward's contact_sum tape.  Up to MFB_BWD_WIDE_MAX_B trajectories (default
+// 512) the four warps of a CTA share one trajectory (SPLIT instantiation): small training batches are bound by the latency of
+// one warp, not by throughput.  Measured on B200 (tools/bwd_crossover.py, T = 500, marv): 2.4 -> 1.3 ms up to B = 128,
+// 2.49 vs 2.23 ms at B = 512, 2.99 vs 3.97 ms at B = 1024.
+static int bwd_wide_max_b() {
+    const char* e = getenv("MFB_BWD_WIDE_MAX_B");
+    return e ? atoi(e) : 512;
+}
+
 template <typename T, int VARIANT>
 static LaunchError launch_sweep(const RolloutArgs<T>& a, const AdjointArgs<T>& g, cudaStream_t st) {
-    const dim3 grid((a.B + kSweepWarps - 1) / kSweepWarps), block(kSweepWarps * 32);
+    const bool wide = a.B <= bwd_wide_max_b();
+    const dim3 grid(wide ? a.B : (a.B + kSweepWarps - 1) / kSweepWarps), block(kSweepWarps * 32);
     const int slots = ((a.N + 31) / 32) * 32;
-    const size_t smem = g.g_cells ? (size_t)kSweepWarps * 3 * slots * sizeof(Quad<T>) : 0;
+    const size_t smem = g.g_cells ? (size_t)(wide ? 1 : kSweepWarps) * 3 * slots * sizeof(Quad<T>) : 0;
     auto go = [&](auto kern) -> LaunchError {
         if (smem > 0 &&
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -41,9 +51,10 @@ static LaunchError launch_sweep(const RolloutArgs<T>& a, const AdjointArgs<T>& g
         return {nullptr};
     };
     if constexpr (VARIANT == kStepLoop) {
-        if (g.g_Fs || g.g_Ff) return go(rollout_bwd_sweep_kernel<T, VARIANT, true>);
+        if (g.g_Fs || g.g_Ff)
+            return wide ? go(rollout_bwd_sweep_kernel<T, VARIANT, true, kSweepWarps>) : go(rollout_bwd_sweep_kernel<T, VARIANT, true, 1>);
     }
-    return go(rollout_bwd_sweep_kernel<T, VARIANT, false>);
+    return wide ? go(rollout_bwd_sweep_kernel<T, VARIANT, false, kSweepWarps>) : go(rollout_bwd_sweep_kernel<T, VARIANT, false, 1>);
 }
 
 template <>

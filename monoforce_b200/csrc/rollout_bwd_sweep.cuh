@@ -211,9 +211,19 @@ __device__ __forceinline__ void reverse_update(const RolloutArgs<T>& a, const Bo
     }
 }
 
-template <typename T, int VARIANT, bool HAS_FGRAD>
+// SPLIT = 1: one warp per trajectory (the throughput shape).  SPLIT = kSweepWarps: the four warps of a CTA share ONE trajectory
+// (small batches: training steps with 16 maps, terrain fitting with a single one, where the call is bound by the latency of
+// one warp walking ~3200 instructions per step).  Warp `sub` visits the point slots j = sub, sub + SPLIT, ...; the per-step
+// sums are combined across the warps through shared memory (two __syncthreads per step, buffers alternating with the step
+// parity) and every warp closes the state adjoint redundantly, so all of them carry identical xb / vb / wb / Rb.
+template <typename T, int VARIANT, bool HAS_FGRAD, int SPLIT = 1>
 __global__ void __launch_bounds__(kSweepWarps * 32, sizeof(T) == 4 ? MFB_SWEEP_MINB : 1)
 rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
+    static_assert(SPLIT == 1 || SPLIT == kSweepWarps, "a trajectory owns one warp or the whole CTA");
+    // SPLIT > 1: per-warp partials of sum f_bar f and of the 24 running sums (one scalar each otherwise: the throughput
+    // instantiation sits exactly at a shared-memory carve-out step with 4 CTAs per SM)
+    __shared__ T xw_c[SPLIT > 1 ? 2 : 1][SPLIT > 1 ? kSweepWarps : 1];
+    __shared__ T xw_s[SPLIT > 1 ? 2 : 1][SPLIT > 1 ? kSweepWarps : 1][SPLIT > 1 ? 24 : 1];
     static_assert(!(VARIANT == kOdeintEuler && HAS_FGRAD), "odeint + force gradients: use the three-pass kernel");
     __shared__ SweepPoints<T> tab;
     __shared__ SweepWarpArea<T> area_all[kSweepWarps];
@@ -225,7 +235,8 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
 
     const int lane = lane_id();
     const int warp = warp_id_pinned();     // opaque: or the compiler re-derives it from S2R %tid all over the point loop
-    const int b = blockIdx.x * kSweepWarps + warp;
+    const int sub = SPLIT > 1 ? warp : 0;                       // which share of the point slots this warp visits
+    const int b = SPLIT > 1 ? (int)blockIdx.x : (int)blockIdx.x * kSweepWarps + warp;
     if (b >= a.B) return;
 
     const long long mi = b / a.map_group;                       // map of this trajectory (groups of consecutive trajectories share one)
@@ -239,11 +250,11 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
     extern __shared__ __align__(16) unsigned char cache_raw[];
     // per contact point one 3-quad record: [0] d/dz of the corners of the point's current cell, [1] d/dfriction of the
     // same corners, [2] (kappa, fx, fy, cell) of the last visit.  48-byte lane stride: conflict-free 16-byte accesses.
-    Quad<T>* const cache = reinterpret_cast<Quad<T>*>(cache_raw) + (size_t)warp * 3 * slots;
+    Quad<T>* const cache = reinterpret_cast<Quad<T>*>(cache_raw) + (size_t)(SPLIT > 1 ? 0 : warp) * 3 * slots;
     if (gcell) {
         Quad<T> zero; zero.v[0] = zero.v[1] = zero.v[2] = zero.v[3] = (T)0;
         Quad<T> none = zero; none.v[3] = pack_cell(-1, (T)0);
-        for (int j = 0; j < ppl; ++j) {
+        for (int j = sub; j < ppl; j += SPLIT) {
             Quad<T>* rec = cache + 3 * (j * 32 + lane);
             quad_store(rec, zero); quad_store(rec + 1, zero); quad_store(rec + 2, none);
         }
@@ -382,7 +393,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
         for (int k = 0; k < 12; ++k) kap[k] = (T)0;
 
 #pragma unroll kSweepUnroll
-        for (int j = 0;; ++j) {
+        for (int j = sub; SPLIT > 1 ? j < ppl : true; j += SPLIT) {
             const uint4 wcst = lds_u4<0>(area_s);
             const T* __restrict__ cells_w = reinterpret_cast<const T*>(((unsigned long long)wcst.y << 32) | wcst.x);
             const int slot = j * 32 + lane;
@@ -577,7 +588,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
                 kap[6] += u1 * px; kap[7] += u1 * py; kap[8] += u1 * pz;
                 kap[9] += kk * px; kap[10] += kk * py; kap[11] += kk * pz;
             }
-            if (j + 1 >= (int)(wcst.w & 0xffu)) break;
+            if (SPLIT == 1 && j + 1 >= (int)(wcst.w & 0xffu)) break;
         }
 
         if (MFB_SWEEP_FRAME_SMEM) {
@@ -598,13 +609,29 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             __syncwarp();
         }
         // C_bar first (one butterfly), so that every lane can close its kappa channel before the big reduction
-        const T C_b = -warp_sum(acc[23]) * (MFB_SWEEP_FRAME_SMEM ? lds_quad<kOffFr + 2 * kQ>(area_s, (T)0).v[3] : invC);
+        T ff_sum = warp_sum(acc[23]);
+        if (SPLIT > 1) {
+            if (lane == 0) xw_c[t & 1][sub] = ff_sum;
+            __syncthreads();
+            ff_sum = (xw_c[t & 1][0] + xw_c[t & 1][1]) + (xw_c[t & 1][2] + xw_c[t & 1][3]);
+        }
+        const T C_b = -ff_sum * (MFB_SWEEP_FRAME_SMEM ? lds_quad<kOffFr + 2 * kQ>(area_s, (T)0).v[3] : invC);
         Cb_prev = C_b;
 #pragma unroll
         for (int i = 0; i < 3; ++i) acc[i] += C_b * kap[i];
 #pragma unroll
         for (int i = 0; i < 9; ++i) acc[9 + i] += C_b * kap[3 + i];
         warp_sum8(acc, lane); warp_sum8(acc + 8, lane); warp_sum8(acc + 16, lane);
+        if (SPLIT > 1) {
+            // every lane holds its warp's 24 totals: lane k < 24 publishes total k, then all lanes add the four warps' rows
+            T mine = acc[0];
+#pragma unroll
+            for (int k = 1; k < 24; ++k) mine = lane == k ? acc[k] : mine;
+            if (lane < 24) xw_s[t & 1][sub][lane] = mine;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 24; ++k) acc[k] = (xw_s[t & 1][0][k] + xw_s[t & 1][1][k]) + (xw_s[t & 1][2][k] + xw_s[t & 1][3][k]);
+        }
 
         // fold the per-point sums into the adjoint of the pre-update state
 #pragma unroll
@@ -623,7 +650,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
             }
             Rb[0] += a0; Rb[3] += a1; Rb[6] += a2;
         }
-        if (g.g_controls && lane == 0) {
+        if (g.g_controls && lane == 0 && sub == 0) {
             g.g_controls[((long long)b * a.nT + t) * 2 + 0] = acc[21];
             g.g_controls[((long long)b * a.nT + t) * 2 + 1] = acc[22];
         }
@@ -641,7 +668,7 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
         T sx = (T)0, sy = (T)0, rr[6] = {0, 0, 0, 0, 0, 0};
         StepFrame<T> f;
         make_frame(f, s, (T)0, (T)0, a.d_max, a.res, a.inv_res);
-        for (int j = 0; j < ppl; ++j) {
+        for (int j = sub; j < ppl; j += SPLIT) {
             const int slot = j * 32 + lane;
             const bool ok = slot < a.N;
             const Quad<T> pq = quad_load(&tab.pp[slot]);
@@ -685,11 +712,23 @@ rollout_bwd_sweep_kernel(const RolloutArgs<T> a, const AdjointArgs<T> g) {
         {
             T red[8] = {sx, sy, rr[0], rr[1], rr[2], rr[3], rr[4], rr[5]};
             warp_sum8(red, lane);
+            if (SPLIT > 1) {
+                __syncthreads();                       // the last step's readers are done with xw_s
+                if (lane < 8) {
+                    T mine = red[0];
+#pragma unroll
+                    for (int k = 1; k < 8; ++k) mine = lane == k ? red[k] : mine;
+                    xw_s[0][sub][lane] = mine;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) red[k] = (xw_s[0][0][k] + xw_s[0][1][k]) + (xw_s[0][2][k] + xw_s[0][3][k]);
+            }
             sx = red[0]; sy = red[1];
 #pragma unroll
             for (int k = 0; k < 6; ++k) rr[k] = red[2 + k];
         }
-        if (lane == 0) {
+        if (lane == 0 && sub == 0) {
             if (g.g_x0) { g.g_x0[b * 3 + 0] = xb[0] + sx; g.g_x0[b * 3 + 1] = xb[1] + sy; g.g_x0[b * 3 + 2] = (T)0; }
             if (g.g_xd0) { g.g_xd0[b * 3 + 0] = vb[0]; g.g_xd0[b * 3 + 1] = vb[1]; g.g_xd0[b * 3 + 2] = vb[2]; }
             if (g.g_om0) { g.g_om0[b * 3 + 0] = wb[0]; g.g_om0[b * 3 + 1] = wb[1]; g.g_om0[b * 3 + 2] = wb[2]; }

@@ -30,12 +30,14 @@ def forward_kernel(request, monkeypatch):
     yield request.param
 
 
-@pytest.fixture(params=["sweep", "three_pass"])
-def adjoint_kernel(request):
-    """Runs an adjoint test once per backward kernel: K2s (single sweep, reads the forward's contact_sum tape)
-    and K2 (three-pass, recomputes it)."""
+@pytest.fixture(params=["sweep", "sweep_wide", "three_pass"])
+def adjoint_kernel(request, monkeypatch):
+    """Runs an adjoint test once per backward kernel: K2s (single sweep, reads the forward's contact_sum tape) with one warp per
+    trajectory, K2s with one CTA per trajectory (the small-batch instantiation; MFB_BWD_WIDE_MAX_B is the batch-size switch) and
+    K2 (three-pass, recomputes the tape)."""
     global ADJOINT_TAPE
-    ADJOINT_TAPE = request.param == "sweep"
+    ADJOINT_TAPE = request.param != "three_pass"
+    monkeypatch.setenv("MFB_BWD_WIDE_MAX_B", str(1 << 30) if request.param == "sweep_wide" else "0")
     yield request.param
     ADJOINT_TAPE = True
 
@@ -556,6 +558,34 @@ def test_graph_replay_of_the_planner_call_matches_eager(variant):
             assert torch.equal(cost_g, sim.last_cost)
     with pytest.raises(ValueError, match="shape"):
         run(controls=ctrls[0][:, :-1])
+
+
+def test_adjoint_kernel_dispatch_by_batch_size(monkeypatch):
+    """Without MFB_BWD_WIDE_MAX_B small batches take the one-CTA-per-trajectory shape of the single-sweep adjoint and large ones
+    the one-warp-per-trajectory shape: d/dcontrols (written without atomics) of the default call is bit-identical to the forced
+    shape it should have picked; the map gradients (accumulated with atomics) agree to round-off."""
+    T = 50
+    sim, cfg = _module("marv", 0.1, T, "step")
+    z0 = hill_map(cfg).to(DEV)[None]
+
+    def run(B, thr):
+        if thr is None:
+            monkeypatch.delenv("MFB_BWD_WIDE_MAX_B", raising=False)
+        else:
+            monkeypatch.setenv("MFB_BWD_WIDE_MAX_B", thr)
+        gen = torch.Generator().manual_seed(B)
+        ctrl = torch.stack([torch.rand(B, 1, generator=gen) * 2 - 1, torch.rand(B, 1, generator=gen) * 2 - 1], -1)
+        ctrl = ctrl.repeat(1, T, 1).to(DEV).requires_grad_(True)
+        z = z0.clone().requires_grad_(True)
+        (Xs, _, Rs, _), _ = sim(z, ctrl)
+        (Xs.sum() + Rs.sum()).backward()
+        return ctrl.grad.clone(), z.grad.clone()
+    for B, picked in ((64, str(1 << 30)), (2048, "0")):
+        (gc_d, gz_d), (gc_w, gz_w), (gc_n, gz_n) = run(B, None), run(B, str(1 << 30)), run(B, "0")
+        gc_f, gz_f = (gc_w, gz_w) if picked != "0" else (gc_n, gz_n)
+        assert torch.equal(gc_d, gc_f), (B, picked)
+        assert not torch.equal(gc_w, gc_n)                                   # different kernels, different association
+        assert rel_err(gc_w, gc_n) < 1e-3 and rel_err(gz_w, gz_n) < 1e-3 and rel_err(gz_d, gz_f) < 1e-4
 
 
 def test_per_trajectory_maps_and_off_map_clamp():

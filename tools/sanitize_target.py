@@ -8,10 +8,12 @@ from helpers_lss import small_cfg, make_inputs
 dev = "cuda"
 for thr, robot, variant in (("0", "marv", False), ("0", "tradr", True), (None, "marv", False), (None, "tradr", True)):
     # both forward kernels: MFB_FWD_WIDE_MAX_B=0 forces one warp per trajectory (K1), unset picks K1w for these small batches
-    if thr is None:
-        os.environ.pop("MFB_FWD_WIDE_MAX_B", None)
-    else:
-        os.environ["MFB_FWD_WIDE_MAX_B"] = thr
+    # (the same switch for the adjoint: MFB_BWD_WIDE_MAX_B, one warp vs one CTA per trajectory in the single-sweep kernel)
+    for var in ("MFB_FWD_WIDE_MAX_B", "MFB_BWD_WIDE_MAX_B"):
+        if thr is None:
+            os.environ.pop(var, None)
+        else:
+            os.environ[var] = thr
     cfg = DPhysConfig(robot=robot, grid_res=0.4); cfg.traj_sim_time, cfg.use_odeint = 0.07, variant
     sim = DPhysics(cfg, device=dev); sim.fused_cost = not variant
     B, T = 5, 7
