@@ -157,6 +157,14 @@ def test_stem_conv_and_upsample_concat_and_cast():
         _close(got, want, max_tol=1e-2, mean_tol=3e-3)
         if Cs:
             assert torch.equal(got[..., :Cs].cpu(), skip)                 # the skip half is a pure copy
+    # odd ratios, a 1-pixel source, and an output SMALLER than the source (cells that own no output pixel): every output pixel is
+    # still written exactly once by the per-source-cell kernel
+    for (Hl, Wl), (H, W) in (((5, 7), (13, 9)), ((1, 1), (6, 4)), ((9, 12), (4, 5)), ((3, 2), (3, 2)), ((7, 5), (1, 11))):
+        low = _bf(torch.randn(2, Hl, Wl, 24, generator=g))
+        skip = _bf(torch.randn(2, H, W, 8, generator=g))
+        got = ops.upsample_concat_nhwc(skip.to(DEV), low.to(DEV), (H, W), 40)
+        _close(got, emul.upsample_concat_nhwc(skip, low, (H, W), 40), max_tol=1e-2, mean_tol=3e-3)
+        assert torch.equal(got[..., :8].cpu(), skip) and float(got[..., 32:].abs().max()) == 0.0
     x = torch.randn(5, 7, 64, generator=g)
     assert torch.equal(ops.cast_bf16(x.to(DEV)).cpu(), x.to(torch.bfloat16))
 
