@@ -4,9 +4,9 @@
 // squeeze-excite branch.
 //
 // Shape of the kernel (measured on B200 at the EfficientNet-B0 layer shapes, tools/dw_bench.py; the cp.async tile / strip kernels
-// it supersedes ran the 16 layers of a 64-image 512x512 batch in 2.40 ms, this one in 1.37 ms):
-//   * a CTA owns an output tile x one channel slab (64 channels = 128-byte rows; 32 channels when 64 would idle > 1/8 of the
-//     lanes: C = 32, 96, 144).  ONE cp.async.bulk.tensor per tile (4-D box; out-of-bounds = the convolution's zero padding,
+// it supersedes ran the 16 layers of a 64-image 512x512 batch in 2.40 ms, this one in 1.29 ms):
+//   * a CTA owns an output tile x one channel slab (64 channels = 128-byte rows; 32 channels when 64 would idle half of the
+//     lanes: C <= 32).  ONE cp.async.bulk.tensor per tile (4-D box; out-of-bounds = the convolution's zero padding,
 //     ragged channel counts zero-filled) brings the whole input patch, double-buffered along a persistent walk over contiguous
 //     (image, slab, tile) ranges: no staging instructions, no bounds arithmetic;
 //   * a thread owns 2 channels x (4 x 4) output pixels (stride 2: 2 x 4): an input pixel is unpacked once (one shift, one mask)
@@ -310,8 +310,10 @@ static int launch_ks(const void* x, const float* w, const float* shift, void* y,
 // x (N,H,W,C) bf16 -> y (N,Ho,Wo,C) bf16; w (K*K, C) fp32 BN-folded, shift (C,) fp32, pool (N,C) fp32 += spatial sums or nullptr
 int launch_dwconv_tma(const void* x, const float* w, const float* shift, void* y, float* pool, int N, int H, int W, int C, int Ho,
                       int Wo, int K, int stride, int pad_h, int pad_w, cudaStream_t st) {
-    // 32-channel slabs when 64-channel ones would idle more than ~1/8 of the lanes (C = 32, 96, 144)
-    const bool narrow = ((C + 63) / 64) * 64 * 100 >= ((C + 31) / 32) * 32 * 115;
+    // 32-channel slabs only when 64-channel ones would idle half of the lanes (C <= 32).  Measured per layer on B200 with both
+    // widths (tools/dw_bench.py): at C = 96 and 144 the 128-byte rows of the wide slabs beat the better lane use of the narrow
+    // ones (config 4: 221 -> 203 us, 227 -> 189 us, 121 -> 115 us), at C = 32 the narrow ones win 129 vs 227 us.
+    const bool narrow = ((C + 63) / 64) * 64 >= 2 * ((C + 31) / 32) * 32;
 #define MFB_DW_ARGS x, w, shift, y, pool, N, H, W, C, Ho, Wo, pad_h, pad_w, st
 #define MFB_DW_CASE(KK, SS)                                                                \
     if (K == KK && stride == SS)                                                           \
