@@ -427,7 +427,7 @@ def block_encoder(dev, steps, cfg4, peaks):
             ev_up[1 - cur].record(copy_stream)
         state["i"] += 1
         return out
-    ms = timed_ms(call, max(steps // 2, 5))
+    ms = timed_ms(call, max(steps, 10), warmup=4)
     gflop_scene = 230.9 if cfg4 else 65.7          # SURVEY.md 8(a) A14 [FlopCounterMode]
     tf = 16 * gflop_scene / ms
     res = {"workload": ("BASELINE config 4 encoder: 16 scenes x 4 cams 512x512 -> 256x256 BEV" if cfg4 else
