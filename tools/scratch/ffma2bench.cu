@@ -36,7 +36,7 @@ int main() {
     float* o; int* io; cudaMalloc(&o, 148 * 16 * 128 * 4); cudaMalloc(&io, 148 * 16 * 128 * 4);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const char* names[4] = {"16 FFMA", "8 FFMA2", "16 FFMA + 8x(xor,add)", "8 FFMA2 + 8x(xor,add)"};
-    for (int blocks_per_sm : {1, 2, 4}) for (int mode = 0; mode < 4; ++mode) {
+    for (int blocks_per_sm : {1, 2, 4, 8}) for (int mode = 0; mode < 4; ++mode) {
         float best = 1e9;
         for (int r = 0; r < 4; ++r) {
             cudaEventRecord(e0);
