@@ -52,7 +52,7 @@ static int launch_v(const CUtensorMap& mx, const CUtensorMap& mw, const Params& 
         return fail_status(MFB_ERR_CUDA, "conv: cudaFuncSetAttribute failed");
     const long long tiles = (long long)p.tiles_w * p.tiles_h * p.N * ((p.Cout + BLOCK_N - 1) / BLOCK_N);
     if (tiles >= (1ll << 31)) return fail_status(MFB_ERR_UNSUPPORTED, "conv: more than 2^31 tiles");
-    const long long resident = 2ll * sm_count();             // persistent: 2 CTAs per SM walk the tiles
+    const long long resident = (BLOCK_N == 256 ? 1ll : 2ll) * sm_count();     // persistent: 2 CTAs per SM walk the tiles (1 for 256-wide tiles)
     dim3 grid((unsigned)(tiles < resident ? tiles : resident));
     kern<<<grid, kThreads, smem, st>>>(mx, mw, p);
     count_launch();
@@ -73,6 +73,16 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p,
     }
     if (!HEAD && k_iters <= 18) return launch_v<BLOCK_N, ACT, false, 2, true, false>(mx, mw, p, st);
     return launch_v<BLOCK_N, ACT, HEAD, 3, false, false>(mx, mw, p, st);
+}
+
+// Deep-K layers whose output channel count is a multiple of 256 (camera / BEV Up convolutions, ResNet layer3): 128 x 256 tiles, one
+// CTA per SM.  At 128 x 128 the tensor pipe waits for shared-memory fills (ncu, camera Up.conv[0]: pipe 50 % busy, the MMA issuer
+// and the epilogue parked on the full / accumulator barriers, L2 hit 95 %): every k-iteration moves 16 KB of activations + 16 KB
+// of weights per 2.1 MFLOP; the wide tile moves 16 + 32 KB per 4.2 MFLOP, a quarter less L2 -> shared-memory traffic per flop.
+template <int ACT>
+static int launch256(const CUtensorMap& mx, const CUtensorMap& mw, const Params& p, cudaStream_t st) {
+    if (p.res) return launch_v<256, ACT, false, 3, false, true>(mx, mw, p, st);
+    return launch_v<256, ACT, false, 3, false, false>(mx, mw, p, st);
 }
 
 }  // namespace conv
@@ -100,7 +110,10 @@ extern "C" int mfb_conv2d_bf16(const mfb_conv_desc* d, const void* x, const void
     if (d->act < kNone || d->act > kSilu) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: unknown activation");
     if (d->Cout > kMaxParamChannels - 128) return fail_status(MFB_ERR_UNSUPPORTED, "conv: at most 1152 output channels");
     if (((uintptr_t)x | (uintptr_t)wgt | (uintptr_t)y | (uintptr_t)residual) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: tensors must be 16-byte aligned");
-    const int block_n = d->Cout > 64 ? 128 : 64;
+    const int k_chunks = d->KH * d->KW * ((d->Cin + kBlockK - 1) / kBlockK);
+    const long long tiles256 = (long long)((d->Wo + kTileW - 1) / kTileW) * ((d->Ho + kTileH - 1) / kTileH) * d->N * (d->Cout / 256);
+    const bool wide_n = !head && k_chunks > 18 && d->Cout % 256 == 0 && tiles256 >= sm_count();   // enough tiles for one CTA per SM
+    const int block_n = wide_n ? 256 : (d->Cout > 64 ? 128 : 64);
     if (((uintptr_t)scale | (uintptr_t)shift) & 15) return fail_status(MFB_ERR_INVALID_ARGUMENT, "conv: scale / shift must be 16-byte aligned");
     if (head) {
         if (d->n_heads > kMaxHeads || d->n_heads * block_n != d->Cout)
@@ -154,6 +167,14 @@ extern "C" int mfb_conv2d_bf16(const mfb_conv_desc* d, const void* x, const void
     if (head) {
         if (d->act != kGelu) return fail_status(MFB_ERR_UNSUPPORTED, "conv: head mode is instantiated for the GELU heads of BevEncode only");
         return block_n == 128 ? launch<128, kGelu, true>(mx, mw, p, st) : launch<64, kGelu, true>(mx, mw, p, st);
+    }
+    if (wide_n) {
+        switch (d->act) {
+            case kNone: return launch256<kNone>(mx, mw, p, st);
+            case kRelu: return launch256<kRelu>(mx, mw, p, st);
+            case kGelu: return launch256<kGelu>(mx, mw, p, st);
+            default: return launch256<kSilu>(mx, mw, p, st);
+        }
     }
     switch (d->act * 2 + (block_n == 128)) {
         case kNone * 2: return launch<64, kNone, false>(mx, mw, p, st);

@@ -14,7 +14,8 @@
 //
 // Layouts: x, y, residual NHWC bf16; wgt [Cout][KH*KW*Cin] bf16 (K-major), optionally one matrix per image (the
 // squeeze-excite scale of an MBConv block folded into its projection weights); scale / shift fp32.
-// Tiling: one CTA = 128 output pixels (TH x TW = 8 x 16 patch of one image) x BLOCK_N output channels.
+// Tiling: one CTA = 128 output pixels (TH x TW = 8 x 16 patch of one image) x BLOCK_N output channels (64, 128, or 256 for the
+// deep-K layers: conv_tcgen05.cu::launch256).
 // The K loop runs over (tap, 64-channel chunk): for each, TMA loads the SHIFTED (and for stride 2: element-strided)
 // activation patch as a 4-D box {64 ch, TW*s, TH*s, 1} with traversal strides {1,s,s,1} (out-of-image rows/columns are
 // zero-filled by the TMA unit == the conv's zero padding; so are the channels beyond Cin when Cin % 64 != 0) and the matching

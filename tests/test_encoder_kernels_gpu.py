@@ -40,6 +40,9 @@ CONV_CASES = [
     ("1x1_project_skip", 2, 16, 26, 672, 112, 1, 1, 0, emul.ACT_NONE, {"per_image": True, "residual": True}),
     ("1x1_narrow_out", 2, 33, 17, 96, 24, 1, 1, 0, emul.ACT_NONE, {}),                    # Cout 24: one 64-column tile, 40 columns masked
     ("3x3_s2_odd",     1, 17, 31, 40, 72, 3, 2, 1, emul.ACT_RELU, {}),                    # odd sizes, Cout % 64 != 0
+    # deep K, Cout % 256 == 0 and at least one tile per SM: the 128 x 256 tile instantiation (one CTA per SM)
+    ("3x3_wide_gelu",  16, 32, 48, 192, 256, 3, 1, 1, emul.ACT_GELU, {}),
+    ("3x3_wide_res",   12, 40, 40, 136, 512, 3, 1, 1, emul.ACT_RELU, {"residual": True}),  # ragged K chunks, ragged tiles, residual
 ]
 
 
