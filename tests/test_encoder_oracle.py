@@ -201,3 +201,37 @@ def test_fast_path_host_logic_matches_module_path_in_fp32(monkeypatch):
         # an in-place weight update must rebuild the folded weights
         be.conv1.weight.mul_(1.1)
         assert encoder_fast.prepare(net) is not P
+
+
+def test_upsample_cell_ownership_partitions_the_output():
+    """The up-sample kernel works per SOURCE cell and finds the output pixels a cell owns with `first_dst`
+    (monoforce_b200/csrc/encoder_ops.cu); restated here in float32: for every (n_in, n_out) each output index belongs to exactly
+    one cell and that cell is the forward mapping src = min(int(r * dst), n_in - 1) of torch's align_corners=True bilinear."""
+    import numpy as np
+    f32 = np.float32
+
+    def src_index(dst, r, n_in):
+        return min(int(f32(r) * f32(dst)), n_in - 1)
+
+    def first_dst(s, r, n_out, n_in):
+        if s <= 0:
+            return 0
+        if r <= 0:
+            return n_out
+        d = min(max(int(np.ceil(f32(s) / f32(r))), 0), n_out)
+        while d > 0 and src_index(d - 1, r, n_in) >= s:
+            d -= 1
+        while d < n_out and src_index(d, r, n_in) < s:
+            d += 1
+        return d
+    for n_in in list(range(1, 40)) + [64, 128, 129]:
+        for n_out in list(range(1, 80)) + [128, 256, 257]:
+            r = f32(n_in - 1) / f32(n_out - 1) if n_out > 1 else f32(0)
+            owner = [-1] * n_out
+            for s in range(n_in):
+                lo = first_dst(s, r, n_out, n_in)
+                hi = first_dst(s + 1, r, n_out, n_in) if s + 1 < n_in else n_out
+                for d in range(lo, hi):
+                    assert owner[d] == -1, (n_in, n_out, d)
+                    owner[d] = s
+            assert owner == [src_index(d, r, n_in) for d in range(n_out)], (n_in, n_out)
